@@ -1,0 +1,129 @@
+/*
+ * b2cnn.h -- C ABI of the B200-native MyCNN forward pass (libb2cnn.so).
+ *
+ * The reference (travistangvh/time-series-kafka-demo) has no plugin/FFI seam: the only
+ * boundary of its hot path is the Python call `output = model(x_arr, a_arr)`
+ * (bin/predictStream.py:157; also bin/utils.py:204,249,682) into `MyCNN.forward`
+ * (bin/models.py:22-36).  These entry points are what a ctypes/cffi binding for that call
+ * binds; INTEGRATION.md shows the stub.  Plain pointers and sizes only -- no torch types.
+ *
+ * Ownership: the caller owns x / age / out / workspace; the library owns only its packed
+ * weight buffers (and, for b2cnn_forward_host, its pinned/device staging buffers).
+ * b2cnn_forward makes no allocation and is asynchronous on `stream`.
+ * Errors: every call returns 0 on success or a B2CNN_E* code; b2cnn_last_error() returns a
+ * thread-local message.  There is no CPU fallback anywhere in this library.
+ */
+#ifndef B2CNN_H_
+#define B2CNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2CNN_OK 0
+#define B2CNN_EINVAL 1      /* bad argument / shape / dtype                                */
+#define B2CNN_EARCH 2       /* architecture outside what the kernels support               */
+#define B2CNN_EVIEW 3       /* L_out(window) != lstm_input: x.view(-1, MAGICNUM) would      */
+                            /* straddle windows (bin/models.py:29) -- rejected, not guessed */
+#define B2CNN_ECUDA 4       /* CUDA runtime / driver error                                  */
+#define B2CNN_ESTATE 5      /* weights not set, workspace too small, ...                    */
+
+enum { B2CNN_DTYPE_F32 = 0, B2CNN_DTYPE_BF16 = 1 };
+/* INDEPENDENT: every window starts from the zero LSTM state == looping the reference one
+ *   window at a time (bin/predictStream.py:70,157).
+ * SEQUENCE: bit-for-bit the structure of model(x_batch): the LSTM scans the batch axis
+ *   (bin/models.py:29-30 with B>1; bin/utils.py:249). */
+enum { B2CNN_MODE_INDEPENDENT = 0, B2CNN_MODE_SEQUENCE = 1 };
+enum { B2CNN_ACT_TANH = 0, B2CNN_ACT_RELU = 1, B2CNN_ACT_IDENTITY = 2 };
+enum { B2CNN_PATH_AUTO = 0, B2CNN_PATH_GENERIC = 1, B2CNN_PATH_TENSORCORE = 2 };
+
+#define B2CNN_FLAG_AFFINE 1 /* per-channel scale/shift after each conv (folded eval-BatchNorm) */
+
+/* Mirrors the constructor of MyCNN (bin/models.py:6-20). */
+typedef struct b2cnn_config {
+    int32_t in_channels; /* conv1 in_channels            models.py:10 (10; 7 in MyCNN2/3)    */
+    int32_t k1;          /* conv1 kernel_size            models.py:10 (10; 5 in MyCNN2/3/4)  */
+    int32_t c_mid;       /* conv1 out_channels           models.py:10 (must be 4)            */
+    int32_t k2;          /* conv2 kernel_size            models.py:11 (5)                    */
+    int32_t pool_k;      /* MaxPool1d kernel_size        models.py:12 (3; 2 in MyCNN2/3/4)   */
+    int32_t pool_s;      /* MaxPool1d stride             models.py:12 (2)                    */
+    int32_t hidden;      /* LSTM hidden_size             models.py:16 (must be 16)           */
+    int32_t layers;      /* LSTM num_layers              models.py:16 (must be 2)            */
+    int32_t window;      /* samples per window W         config.cfg:23 (120)                 */
+    int32_t lstm_input;  /* MAGICNUM                     models.py:8  (must equal L_out(W))  */
+    int32_t act;         /* B2CNN_ACT_*; the reference uses tanh (models.py:23,26)           */
+    int32_t flags;       /* B2CNN_FLAG_*                                                     */
+    float age_coef;      /* models.py:32 (1e-8)                                              */
+    int32_t device;      /* CUDA device ordinal, or -1 for the current device                */
+} b2cnn_config;
+
+typedef struct b2cnn_handle b2cnn_handle;
+
+/* L_out(W): conv1 -> pool -> conv2 -> pool output length (floor pooling); <=0 if invalid. */
+int64_t b2cnn_l_out(const b2cnn_config *cfg);
+
+/* Number of floats in the packed weight blob, in this order (== state_dict order of the
+ * used tensors, bin/models.py:10-17):
+ *   conv1.weight[4][C][K1], conv1.bias[4], conv2.weight[1][4][K2], conv2.bias[1],
+ *   lstm.weight_ih_l0[64][L], lstm.weight_hh_l0[64][16], lstm.bias_ih_l0[64], lstm.bias_hh_l0[64],
+ *   lstm.weight_ih_l1[64][16], lstm.weight_hh_l1[64][16], lstm.bias_ih_l1[64], lstm.bias_hh_l1[64],
+ *   out.weight[16], out.bias[1]
+ *   (+ if B2CNN_FLAG_AFFINE: scale1[4], shift1[4], scale2[1], shift2[1]) */
+int64_t b2cnn_weight_count(const b2cnn_config *cfg);
+
+/* Replaces `model = torch.load(path); model.eval()` (bin/predictStream.py:36-37). */
+int b2cnn_create(const b2cnn_config *cfg, b2cnn_handle **out);
+void b2cnn_destroy(b2cnn_handle *h);
+
+/* Replaces load_state_dict: copies the packed blob (host or device memory) into the
+ * library's device buffers, enqueued on `stream` (a cudaStream_t, may be NULL). */
+int b2cnn_set_weights(b2cnn_handle *h, const float *blob, int64_t n_floats, int blob_on_device,
+                      void *stream);
+
+/* Bytes of caller-provided device scratch b2cnn_forward needs for a batch of B windows. */
+int64_t b2cnn_workspace_bytes(b2cnn_handle *h, int64_t B, int mode);
+
+/* Replaces `output = model(x, age)` (bin/predictStream.py:157).  All pointers are DEVICE
+ * pointers.  x: [B][C][W] contiguous, dtype f32 or bf16.  age: n_age == B or 1 (broadcast).
+ * out: [B] floats: the logit (bin/models.py:34), or sigmoid(logit) if apply_sigmoid
+ * (bin/predictStream.py:160). */
+int b2cnn_forward(b2cnn_handle *h, const void *x, int dtype, int64_t B, const float *age,
+                  int64_t n_age, int mode, int apply_sigmoid, float *out, void *workspace,
+                  int64_t workspace_bytes, void *stream);
+
+/* Same call with HOST pointers (ideally pinned): chunked H2D copy of x overlapped with
+ * compute, D2H of the B results; synchronous on return.  Uses library-owned staging. */
+int b2cnn_forward_host(b2cnn_handle *h, const void *x_host, int dtype, int64_t B,
+                       const float *age_host, int64_t n_age, int mode, int apply_sigmoid,
+                       float *out_host);
+
+/* Intermediate of bin/models.py:29 (after the second pool, before the LSTM):
+ * feats[B][L_out] floats on the device.  For parity tests. */
+int b2cnn_features(b2cnn_handle *h, const void *x, int dtype, int64_t B, float *feats,
+                   void *stream);
+
+/* Options: "path" = B2CNN_PATH_*; "tc_splits" = 2|3 (bf16 pieces per fp32 conv1 weight);
+ * "profile" = 0|1: record CUDA events around the stages of each b2cnn_forward on its stream. */
+int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value);
+int64_t b2cnn_get_option(b2cnn_handle *h, const char *key);
+
+/* Kernel launches issued by the most recent forward on this handle (bench: gpu_launches),
+ * and which path it took (B2CNN_PATH_GENERIC / B2CNN_PATH_TENSORCORE). */
+int64_t b2cnn_last_launch_count(b2cnn_handle *h);
+int b2cnn_last_path(b2cnn_handle *h);
+
+/* With option "profile"=1: device time in ms of a stage of the most recent b2cnn_forward
+ * (0 = front end conv/pool kernel(s), the dominant kernel; 1 = projection + LSTM head).
+ * Synchronises on the stage's end event.  <0 if unavailable. */
+double b2cnn_last_stage_ms(b2cnn_handle *h, int stage);
+
+const char *b2cnn_last_error(void);
+const char *b2cnn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2CNN_H_ */

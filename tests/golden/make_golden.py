@@ -1,0 +1,163 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the authoring container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+What is executed is the reference's own code: ``bin/models.py`` (class ``MyCNN`` and its
+``forward``), the shipped checkpoints ``model/MyCNN{2,3,4,5}.pth``, the fixture
+``explore_output/X.TESTINPUT`` and (verbatim, with stub modules for the absent ``wfdb`` /
+``pyspark`` imports) ``bin/utils.py``'s ``create_batch`` / ``get_arr`` / ``run_model``.
+Nothing from this repo's oracle/ or product code is used to produce the expected values.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.nn as nn
+
+warnings.filterwarnings("ignore")
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REF, "bin"))
+from models import MyCNN  # noqa: E402  (the reference class)
+
+import __main__  # noqa: E402
+
+__main__.MyCNN = MyCNN  # the legacy pickles name their class "__main__.MyCNN"
+
+
+def sd_arrays(m):
+    return {"sd." + k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+
+
+def load_ckpt(n):
+    m = torch.load(f"{REF}/model/MyCNN{n}.pth", weights_only=False, map_location="cpu")
+    m.eval()
+    return m
+
+
+@torch.no_grad()
+def loop(m, x, a):
+    return torch.cat([m(x[i:i + 1], a[i:i + 1]) for i in range(x.shape[0])])
+
+
+@torch.no_grad()
+def features(m, x):
+    x = torch.tanh(m.conv1(x)); x = m.pool(x)
+    x = torch.tanh(m.conv2(x)); x = m.pool(x)
+    return x.view(-1, m.MAGICNUM)
+
+
+# ---------------------------------------------------------------- 1. MyCNN5 + X.TESTINPUT
+def golden_mycnn5():
+    m = load_ckpt(5)
+    df = pd.read_csv(f"{REF}/explore_output/X.TESTINPUT")
+    x64 = np.swapaxes(df.values[None], 1, 2)            # utils.py:538 (n,120,10)->(n,10,120)
+    x = torch.from_numpy(x64).type(torch.FloatTensor)   # predictStream.py:155
+    out = {}
+    with torch.no_grad():
+        for age in (50.0, 65.0):
+            a = torch.tensor([age])
+            o = m(x, a)
+            out[f"logit_age{int(age)}"] = o.numpy()
+            out[f"prob_age{int(age)}"] = torch.sigmoid(o).numpy()
+        out["features"] = features(m, x).numpy()
+        # the notebook cell (explore_torch.ipynb:4277-4310) prints [[0.5668570399284363]]
+        out["notebook_print"] = np.array([[0.5668570399284363]])
+        # batched calls: random "vital-sign-like" windows, seed 0 (SURVEY section 4 probe)
+        torch.manual_seed(0)
+        xb = torch.randn(8, 10, 120) * 20 + 50
+        ab = torch.tensor([15., 30., 45., 50., 65., 70., 80., 20.])
+        out["xb"] = xb.numpy(); out["ab"] = ab.numpy()
+        out["xb_seq_logits"] = m(xb, ab).numpy()          # utils.py:249 semantics
+        out["xb_ind_logits"] = loop(m, xb, ab).numpy()    # predictStream.py:157 semantics
+        torch.manual_seed(1)
+        xn = torch.randn(8, 10, 120)
+        out["xn"] = xn.numpy()
+        out["xn_seq_logits"] = m(xn, ab).numpy()
+        out["xn_ind_logits"] = loop(m, xn, ab).numpy()
+        out["xn_features"] = features(m, xn).numpy()
+    # verbatim utils.run_model (utils.py:671-692)
+    for name in ("wfdb", "pyspark", "pyspark.sql"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pyspark.sql"].SparkSession = object
+    cwd = os.getcwd(); os.chdir(REF)
+    try:
+        import utils as ref_utils
+        y_pred, y_prob = ref_utils.run_model(m, torch.device("cpu"), df, 50.0)
+    finally:
+        os.chdir(cwd)
+    out["run_model_pred"] = np.array(y_pred); out["run_model_prob"] = np.array(y_prob, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "mycnn5_xtestinput.npz"), x=x.numpy(), x_f64=x64,
+                        **sd_arrays(m), **out)
+    print("mycnn5:", out["logit_age50"], out["prob_age50"], y_pred, y_prob)
+
+
+# ---------------------------------------------------------------- 2. older checkpoints
+def golden_old_ckpts():
+    for n in (2, 3, 4):
+        m = load_ckpt(n)
+        C = m.conv1.in_channels
+        m.MAGICNUM = m.lstm.input_size           # models.py needs the attribute (27 here)
+        torch.manual_seed(10 + n)
+        xb = torch.randn(6, C, 120) * 20 + 50
+        ab = torch.tensor([15., 30., 45., 50., 65., 80.])
+        with torch.no_grad():
+            seq = m(xb, ab).numpy()               # bin/models.py forward => age coef 1e-8
+            ind = loop(m, xb, ab).numpy()
+            f = features(m, xb).numpy()
+        meta = np.array([C, m.conv1.kernel_size[0], m.conv2.kernel_size[0], m.pool.kernel_size,
+                         m.pool.stride, m.lstm.input_size])
+        np.savez_compressed(os.path.join(OUT, f"mycnn{n}_ckpt.npz"), xb=xb.numpy(), ab=ab.numpy(),
+                            seq_logits_coef1e8=seq, ind_logits_coef1e8=ind, features=f, meta=meta,
+                            **sd_arrays(m))
+        print(f"mycnn{n}:", meta, ind[:3])
+
+
+# ---------------------------------------------------------------- 3. stretched architectures
+def stretched(kind, C, W, seed):
+    """the reference class with conv1/lstm/MAGICNUM re-instantiated."""
+    torch.manual_seed(seed)
+    g = MyCNN()
+    if kind == "mycnn5":
+        k1, pk, ps = 10, 3, 2
+    else:
+        k1, pk, ps = 5, 2, 2
+        g.pool = nn.MaxPool1d(kernel_size=pk, stride=ps)
+    l1 = W - k1 + 1; p1 = (l1 - pk) // ps + 1; l2 = p1 - 5 + 1; L = (l2 - pk) // ps + 1
+    g.MAGICNUM = L
+    g.conv1 = nn.Conv1d(C, 4, k1)
+    g.lstm = nn.LSTM(L, 16, 2)
+    g.eval()
+    return g, L
+
+
+def golden_stretched():
+    cases = [("mycnn5", 3, 1500, 4, 0), ("mycnn3", 3, 1500, 4, 0),
+             ("mycnn3", 3, 7500, 1, 0),      # BASELINE.json configs[0]: [1,3,7500] fp32
+             ("mycnn5", 3, 7500, 2, 0)]
+    for kind, C, W, B, seed in cases:
+        g, L = stretched(kind, C, W, seed)
+        torch.manual_seed(1)
+        x = torch.randn(B, C, W)
+        age = torch.linspace(15, 80, B) if B > 1 else torch.tensor([65.0])
+        xbf = x.to(torch.bfloat16).float()       # bf16-representable copy (config 2 dtype)
+        with torch.no_grad():
+            rec = dict(x=x.numpy(), age=age.numpy(), L=np.array(L),
+                       seq_logits=g(x, age).numpy(), ind_logits=loop(g, x, age).numpy(),
+                       features=features(g, x).numpy(),
+                       bf16_ind_logits=loop(g, xbf, age).numpy())
+        np.savez_compressed(os.path.join(OUT, f"stretched_{kind}_c{C}_w{W}_b{B}.npz"),
+                            **rec, **sd_arrays(g))
+        print(kind, C, W, B, "L_out", L, rec["ind_logits"][:2])
+
+
+if __name__ == "__main__":
+    golden_mycnn5()
+    golden_old_ckpts()
+    golden_stretched()

@@ -1,0 +1,131 @@
+"""CPU: host-side logic of the drop-in -- checkpoint loading, state_dict contract, arch
+inference, the C-ABI library's exported symbols -- and that the product path fails loudly
+(no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import tskd_b200
+from tskd_b200 import capi
+from tskd_b200.arch import BLOB_KEYS, INERT_KEYS, ArchConfig, arch_from_state_dict
+from conftest import ROOT, load_golden
+
+REF_MODELS = "/root/reference/model"
+
+
+def test_library_exports_every_declared_symbol():
+    lib = tskd_b200.load_library()
+    header = open(os.path.join(ROOT, "include", "b2cnn.h")).read()
+    declared = set(re.findall(r"\b(b2cnn_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.b2cnn_version()
+
+
+def test_pure_host_entry_points():
+    lib = tskd_b200.load_library()
+    cfg = capi.make_config(tskd_b200.ARCH_PRESETS["mycnn5"])
+    assert lib.b2cnn_l_out(ctypes.byref(cfg)) == 25
+    assert lib.b2cnn_weight_count(ctypes.byref(cfg)) == 5370   # 5957 params minus the unused out1/out2/age_fn
+    big = capi.make_config(tskd_b200.ARCH_PRESETS["mycnn5"].with_shape(3, 75000))
+    assert lib.b2cnn_l_out(ctypes.byref(big)) == 18745
+    old = capi.make_config(tskd_b200.ARCH_PRESETS["mycnn3"].with_shape(3, 75000))
+    assert lib.b2cnn_l_out(ctypes.byref(old)) == 18747
+    bad = capi.make_config(ArchConfig(window=12))
+    assert lib.b2cnn_l_out(ctypes.byref(bad)) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_fails_loudly_without_gpu():
+    lib = tskd_b200.load_library()
+    cfg = capi.make_config(tskd_b200.ARCH_PRESETS["mycnn5"])
+    h = ctypes.c_void_p()
+    rc = lib.b2cnn_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == capi.ECUDA and not h.value
+    assert b"cuda" in lib.b2cnn_last_error().lower()
+    m = tskd_b200.B200MyCNN()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 10, 120), torch.tensor([50.0]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.predict(torch.zeros(4, 10, 120))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "time-series-kafka-demo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("oracle/mycnn_torch.py", ""), f
+
+
+def test_state_dict_contract(golden5):
+    g, sd = golden5
+    m = tskd_b200.B200MyCNN.from_reference(sd)
+    assert m.arch == tskd_b200.ARCH_PRESETS["mycnn5"] and m.MAGICNUM == 25
+    out = m.state_dict()
+    assert list(out.keys()) == list(sd.keys())             # same names, same order
+    for k in sd:
+        assert out[k].shape == sd[k].shape and torch.equal(out[k], sd[k]), k
+    assert set(BLOB_KEYS) | set(INERT_KEYS) == set(sd.keys())
+    assert sum(v.numel() for v in sd.values()) == 5957      # explore_torch.ipynb:2117
+    blob = m.packed_weights()
+    assert blob.numel() == 5370
+    assert torch.equal(blob[:400], sd["conv1.weight"].reshape(-1))
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({k: v for k, v in sd.items() if k != "out.bias"})
+    assert m.training is False
+    with pytest.raises(NotImplementedError):
+        m.train()
+    assert m.eval() is m
+
+
+@pytest.mark.parametrize("n,C,k1,pk,L", [(2, 7, 5, 2, 27), (3, 7, 5, 2, 27), (4, 10, 5, 2, 27)])
+def test_arch_inference_older_checkpoints(n, C, k1, pk, L):
+    g, sd = load_golden(f"mycnn{n}_ckpt.npz")
+    a = arch_from_state_dict(sd, window=120)
+    assert (a.in_channels, a.k1, a.pool_k, a.pool_s, a.l_out) == (C, k1, pk, 2, L)
+    m = tskd_b200.B200MyCNN.from_reference(sd)
+    assert "out1.weight" not in m.state_dict() and "age_fn.weight" in m.state_dict()
+
+
+def test_view_contract_rejected():
+    """L_out(window) != MAGICNUM must be an error, not a silent straddle (bin/models.py:29)."""
+    g, sd = load_golden("mycnn5_xtestinput.npz")
+    with pytest.raises((RuntimeError, ValueError)):
+        tskd_b200.B200MyCNN.from_reference(sd, window=240)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MODELS), reason="reference checkpoints only exist in the authoring container")
+@pytest.mark.parametrize("n", [2, 3, 4, 5])
+def test_load_legacy_pickles(n):
+    ref = tskd_b200.load_reference_checkpoint(f"{REF_MODELS}/MyCNN{n}.pth")
+    assert type(ref).__name__ == "PickledMyCNN" and ref.training is False
+    m = tskd_b200.B200MyCNN.from_reference(ref)
+    g, sd = load_golden("mycnn5_xtestinput.npz" if n == 5 else f"mycnn{n}_ckpt.npz")
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_restricted_unpickler_rejects_foreign_globals(tmp_path):
+    import pickle
+    p = tmp_path / "evil.pth"
+    with open(p, "wb") as f:
+        pickle.dump(os.system, f)
+    with pytest.raises(Exception):
+        tskd_b200.load_reference_checkpoint(str(p))
+
+
+def test_synth_is_deterministic():
+    a = tskd_b200.synth.make_windows(5, 3, 64, "physio", seed=1)
+    b = tskd_b200.synth.make_windows(5, 3, 64, "physio", seed=1)
+    assert torch.equal(a, b) and a.min() >= 0 and a.max() <= 200
+    e = tskd_b200.synth.make_windows(4, 3, 64, "edge", seed=1)
+    assert torch.isnan(e[0]).any() and torch.isinf(e[1]).any()
+    ages = tskd_b200.synth.make_ages(100)
+    assert ages.min() >= 15 and ages.max() <= 80

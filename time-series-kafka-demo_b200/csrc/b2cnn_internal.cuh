@@ -1,0 +1,96 @@
+// b2cnn_internal.cuh -- shared declarations of libb2cnn (sm_100a only).
+//
+// The hot path being replaced is MyCNN.forward (/root/reference/bin/models.py:22-36):
+//   conv1+tanh (:23) -> pool (:24) -> [dropout = identity in eval (:25)] -> conv2+tanh (:26)
+//   -> pool (:27) -> view(-1, MAGICNUM) (:29) -> 2-layer LSTM (:30) -> Linear (:31)
+//   -> * relu(age*1e-8+1) (:32-33) -> squeeze (:34)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2cnn.h"
+
+namespace b2cnn {
+
+constexpr int kCMid = 4;      // conv1 out_channels (models.py:10)
+constexpr int kHidden = 16;   // LSTM hidden (models.py:16)
+constexpr int kGates = 64;    // 4 * hidden, PyTorch gate order i,f,g,o
+constexpr int kMaxW1 = 800;   // 4 * C * K1 floats kept in the kernel-parameter constant bank
+constexpr int kMaxK2 = 8;
+
+// Everything derived from b2cnn_config (see RefArch in oracle/mycnn_torch.py for the mirror).
+struct Dims {
+    int C, K1, K2, PK, PS, W;
+    int L1, P1, L2, L;       // conv1 out, pool1 out, conv2 out, pool2 out (= LSTM input size)
+    int act, has_affine;
+    float age_coef;
+};
+
+// Conv weights travel as a by-value kernel parameter: they land in the constant bank, so the
+// fully unrolled FFMAs of the templated kernels read them as c[0x0][imm] operands.
+struct ConvWeights {
+    float w1[kMaxW1];          // [c][k][o]  -> (c*K1 + k)*4 + o
+    float b1[kCMid];
+    float w2[kCMid * kMaxK2];  // [c][k]     -> c*K2 + k
+    float b2;
+    float s1[kCMid], t1[kCMid], s2, t2;   // optional conv-epilogue affine (folded eval-BN)
+};
+
+// Small LSTM / head tensors: device pointers into the handle's copy of the packed blob.
+struct HeadWeights {
+    const float *wih0T;   // [L][64]  transposed copy of lstm.weight_ih_l0
+    const float *whh0;    // [64][16]
+    const float *bih0, *bhh0;
+    const float *wih1, *whh1;   // [64][16]
+    const float *bih1, *bhh1;
+    const float *wo, *bo;       // out.weight[16], out.bias[1]
+};
+
+struct FrontParams {
+    const void *x;        // [B][C][W] f32 or bf16
+    float *feats;         // features, element (b, p) at feats[b*sB + p*sP]
+    int64_t sB, sP;
+    int B;
+    int tile_p;           // final positions per tile
+    int n_tiles;
+    Dims d;
+    int xs_stride, a1_stride;   // padded smem row strides (floats)
+    ConvWeights cw;
+};
+
+// NaN-propagating max, as ATen's max_pool1d ((v > m) || isnan(v)); fmaxf would drop NaNs.
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == B2CNN_ACT_TANH) return tanhf(v);
+    if (act == B2CNN_ACT_RELU) return (v > 0.f || v != v) ? v : 0.f;
+    return v;
+}
+
+__device__ __forceinline__ float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// conflict-free smem index for "thread r reads a window starting at stride*r": one pad word
+// every 32 keeps lanes of a warp on distinct banks for strides 4 and 8.
+__host__ __device__ __forceinline__ int padi(int g) { return g + (g >> 5); }
+
+// ---- launchers (b2cnn_generic.cu / b2cnn_head.cu) ----------------------------------------
+// Each returns the number of kernels it launched, or <0 with the message in `err`.
+int launch_frontend_generic(const Dims &d, const ConvWeights &cw, const void *x, int dtype,
+                            int64_t B, float *feats, int64_t sB, int64_t sP, cudaStream_t st,
+                            int num_sms, const char **err);
+
+int launch_head(const Dims &d, const HeadWeights &hw, const float *feats, int64_t sB, int64_t sP,
+                int64_t B, const float *age, int64_t n_age, int mode, int apply_sigmoid,
+                float *out, float *gates_ws, float *partial_ws, int ksplit, cudaStream_t st,
+                const char **err);
+
+int choose_ksplit(int64_t B, int L, int num_sms);
+
+void launch_transpose_wih(const float *wih0, float *wih0T, int L, cudaStream_t st);
+
+}  // namespace b2cnn

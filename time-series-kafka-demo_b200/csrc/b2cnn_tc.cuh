@@ -1,0 +1,28 @@
+// b2cnn_tc.cuh -- interface of the tcgen05 (5th-gen tensor core) fast path, b2cnn_tc.cu.
+#pragma once
+#include "b2cnn_internal.cuh"
+
+namespace b2cnn {
+
+struct TcState {
+    bool ready = false;
+    int splits = 3;
+    void *d_bmats = nullptr;     // Toeplitz-expanded conv1 weights, bf16 pieces (see b2cnn_tc.cu)
+    void *tmap_storage = nullptr;
+};
+
+const char *tc_error();
+int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_wih0, const HeadWeights &hw,
+               int splits, int num_sms, cudaStream_t st);
+void tc_release(TcState &s);
+bool tc_supported(const TcState &s, const Dims &d, int dtype, int64_t B, int mode);
+bool tc_can_emit_features(const TcState &s);
+int64_t tc_workspace_bytes(const TcState &s, const Dims &d, int64_t B);
+// returns number of kernel launches, or <0 with *err set
+int tc_forward(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
+               const float *age, int64_t n_age, int apply_sigmoid, float *out, float *feats, float *partial,
+               float *gates, void *tc_ws, int num_sms, cudaStream_t st, const char **err);
+int tc_features(TcState &s, const Dims &d, const void *x, int64_t B, float *feats, int num_sms, cudaStream_t st,
+                const char **err);
+
+}  // namespace b2cnn
