@@ -1,0 +1,102 @@
+"""GPU: the tcgen05 / TMA front end (b2cnn_tc.cu) against the PyTorch-CPU oracle and against
+the exact generic kernel.  path="tensorcore" makes the library refuse instead of falling back,
+so a pass here is a pass of the tensor-core kernel itself."""
+from dataclasses import replace
+
+import numpy as np
+import pytest
+import torch
+
+import tskd_b200
+from conftest import rel_err
+from oracle import mycnn_torch as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+def _pair(C, W, path="tensorcore", tc_splits=3, seed=0):
+    oarch = O.stretched(O.ARCH_MYCNN5, C, W)
+    ref = O.make_ref(oarch, seed=seed)
+    m = tskd_b200.B200MyCNN(tskd_b200.ARCH_PRESETS["mycnn5"].with_shape(C, W), path=path, tc_splits=tc_splits).to(DEV)
+    m.load_state_dict(ref.state_dict())
+    return ref, m
+
+
+@pytest.mark.parametrize("C,W,B,dist", [
+    (3, 1528, 5, "normal"), (3, 7504, 128, "normal"), (3, 7504, 200, "physio"),
+    (1, 2048, 130, "normal"), (2, 4000, 64, "normal"), (4, 3000, 257, "physio"),
+    (3, 75000, 9, "normal"),
+])
+def test_tc_features_and_logits(C, W, B, dist):
+    ref, m = _pair(C, W)
+    x = tskd_b200.synth.make_windows(B, C, W, dist, seed=21, dtype=torch.bfloat16)
+    ages = tskd_b200.synth.make_ages(B, seed=21)
+    fw = O.ref_features(ref, x.float()).numpy()
+    fg = m.features(x.to(DEV)).cpu().numpy()
+    assert m.last_path == "tensorcore"
+    err = np.abs(fg - fw)
+    assert err.max() < 2e-5, (err.max(), np.unravel_index(err.argmax(), err.shape))
+    want = O.ref_independent(ref, x.float(), ages).numpy()
+    got = m.predict(x.to(DEV), ages.to(DEV)).cpu().numpy()
+    assert m.last_path == "tensorcore" and rel_err(got, want) <= TOL, rel_err(got, want)
+
+
+def test_tc_sequence_mode():
+    ref, m = _pair(3, 1528)
+    x = tskd_b200.synth.make_windows(40, 3, 1528, "normal", seed=6, dtype=torch.bfloat16)
+    ages = tskd_b200.synth.make_ages(40, seed=6)
+    want = O.ref_sequence(ref, x.float(), ages).numpy()
+    got = m(x.to(DEV), ages.to(DEV)).cpu().numpy()
+    assert m.last_path == "tensorcore" and rel_err(got, want) <= TOL
+
+
+def test_tc_matches_generic_kernel():
+    _, mt = _pair(3, 7504, path="tensorcore")
+    _, mg = _pair(3, 7504, path="generic")
+    x = tskd_b200.synth.make_windows(300, 3, 7504, "normal", seed=8, dtype=torch.bfloat16).to(DEV)
+    ft, fg = mt.features(x), mg.features(x)
+    assert mt.last_path == "tensorcore" and mg.last_path == "generic"
+    assert (ft - fg).abs().max().item() < 5e-6
+    ages = tskd_b200.synth.make_ages(300, seed=8).to(DEV)
+    assert rel_err(mt.predict(x, ages).cpu().numpy(), mg.predict(x, ages).cpu().numpy()) < 2e-5
+
+
+def test_tc_two_piece_weights_still_inside_tolerance():
+    ref, m2 = _pair(3, 7504, tc_splits=2)
+    x = tskd_b200.synth.make_windows(128, 3, 7504, "normal", seed=12, dtype=torch.bfloat16)
+    ages = tskd_b200.synth.make_ages(128, seed=12)
+    want = O.ref_independent(ref, x.float(), ages).numpy()
+    got = m2.predict(x.to(DEV), ages.to(DEV)).cpu().numpy()
+    assert m2.last_path == "tensorcore" and rel_err(got, want) <= TOL
+
+
+def test_tc_nan_inf_windows_are_recomputed_exactly():
+    """Band zeros turn inf/NaN samples into NaN blocks; flagged windows are recomputed by the
+    exact kernel so the result has the reference's NaN pattern (+inf saturates, NaN propagates)."""
+    ref, m = _pair(3, 7504)
+    x = tskd_b200.synth.make_windows(140, 3, 7504, "edge", seed=4, dtype=torch.bfloat16)
+    x[77, 1, 7503] = float("inf")
+    x[139, 2, 0] = float("nan")
+    ages = torch.full((140,), 65.0)
+    want = O.ref_independent(ref, x.float(), ages).numpy()
+    got = m.predict(x.to(DEV), ages.to(DEV)).cpu().numpy()
+    assert m.last_path == "tensorcore"
+    assert np.array_equal(np.isnan(want), np.isnan(got))
+    assert np.isnan(want[0]) and np.isfinite(want[1]) and np.isfinite(want[77]) and np.isnan(want[139])
+    ok = ~np.isnan(want)
+    assert rel_err(got[ok], want[ok]) <= TOL
+    fw = O.ref_features(ref, x.float()).numpy()
+    fg = m.features(x.to(DEV)).cpu().numpy()
+    assert np.array_equal(np.isnan(fw), np.isnan(fg))
+    assert np.nanmax(np.abs(fg - fw)) < 2e-5
+
+
+def test_tc_refuses_unsupported_shapes_instead_of_falling_back():
+    _, m = _pair(3, 7500)            # 7500 % 8 != 0: rows are not 16-byte aligned for TMA
+    with pytest.raises(RuntimeError, match="tensor"):
+        m.predict(torch.zeros(4, 3, 7500, dtype=torch.bfloat16, device=DEV))
+    _, m = _pair(3, 7504)
+    with pytest.raises(RuntimeError, match="tensor"):
+        m.predict(torch.zeros(4, 3, 7504, dtype=torch.float32, device=DEV))   # fp32 input

@@ -226,14 +226,8 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
     (void)ws_bytes;
     const char *err = "";
     int launches = 0;
-    if (use_tc(h, dtype, B, mode)) {
-        int n = tc_forward(h->tc, d, h->cw, h->hw, x, B, age, n_age, apply_sigmoid, out, feats, partial, gates, tc_ws,
-                           h->num_sms, st, &err);
-        if (n < 0) return fail(B2CNN_ECUDA, std::string("tensor-core path: ") + err);
-        h->last_launches = n; h->last_path = B2CNN_PATH_TENSORCORE;
-        return B2CNN_OK;
-    }
-    if (h->opt_path == B2CNN_PATH_TENSORCORE)
+    const bool tc = use_tc(h, dtype, B, mode);
+    if (!tc && h->opt_path == B2CNN_PATH_TENSORCORE)
         return fail(B2CNN_EARCH, "path=tensorcore requested but this shape/dtype/mode is not supported by the tcgen05 kernel");
     const bool prof = h->opt_profile != 0;
     if (prof) {
@@ -241,15 +235,25 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
             if (!h->ev_stage[i]) CU_TRY(cudaEventCreate(&h->ev_stage[i]));
         CU_TRY(cudaEventRecord(h->ev_stage[0], st));
     }
-    int n = launch_frontend_generic(d, h->cw, x, dtype, B, feats, d.L, 1, st, h->num_sms, &err);
-    if (n < 0) return fail(B2CNN_ECUDA, std::string("front end: ") + err);
+    // feature layout: the generic kernel writes rows [B][L]; the tensor-core kernel's threads
+    // are windows, so it writes the transpose [L][B] (coalesced across lanes).
+    int64_t sB = d.L, sP = 1;
+    int n;
+    if (tc) {
+        sB = 1; sP = B;
+        n = tc_frontend(h->tc, d, h->cw, x, B, feats, sB, sP, tc_ws, h->num_sms, st, &err);
+        if (n < 0) return fail(B2CNN_ECUDA, std::string("tensor-core front end: ") + err);
+    } else {
+        n = launch_frontend_generic(d, h->cw, x, dtype, B, feats, sB, sP, st, h->num_sms, &err);
+        if (n < 0) return fail(B2CNN_ECUDA, std::string("front end: ") + err);
+    }
     launches += n;
     if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
-    n = launch_head(d, h->hw, feats, d.L, 1, B, age, n_age, mode, apply_sigmoid, out, gates, partial, ks, st, &err);
+    n = launch_head(d, h->hw, feats, sB, sP, B, age, n_age, mode, apply_sigmoid, out, gates, partial, ks, st, &err);
     if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
     launches += n;
     if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }
-    h->last_launches = launches; h->last_path = B2CNN_PATH_GENERIC;
+    h->last_launches = launches; h->last_path = tc ? B2CNN_PATH_TENSORCORE : B2CNN_PATH_GENERIC;
     return B2CNN_OK;
 }
 
@@ -281,7 +285,7 @@ extern "C" int b2cnn_features(b2cnn_handle *h, const void *x, int dtype, int64_t
     const char *err = "";
     int n;
     if (use_tc(h, dtype, B, B2CNN_MODE_INDEPENDENT) && tc_can_emit_features(h->tc)) {
-        n = tc_features(h->tc, h->d, x, B, feats, h->num_sms, (cudaStream_t)stream, &err);
+        n = tc_features(h->tc, h->d, h->cw, x, B, feats, h->num_sms, (cudaStream_t)stream, &err);
         h->last_path = B2CNN_PATH_TENSORCORE;
     } else {
         if (h->opt_path == B2CNN_PATH_TENSORCORE) return fail(B2CNN_EARCH, "b2cnn_features: tensor-core path unavailable for this shape");

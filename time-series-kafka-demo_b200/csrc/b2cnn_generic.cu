@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(256, 2) frontend_kernel(const __grid_constant_
     const int n_runs2 = (tp + 1) / 2;
     const int act = p.d.act, aff = p.d.has_affine;
 
-    for (int b = blockIdx.y; b < p.B; b += gridDim.y) {
+    const int nwin = p.win_count ? *p.win_count : p.B;
+    for (int wi = blockIdx.y; wi < nwin; wi += gridDim.y) {
+        const int b = p.win_list ? p.win_list[wi] : wi;
         // ---- stage 1: input tile -> smem (fp32) ------------------------------------------
         const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * W + i0;
         for (int c = 0; c < C; ++c) {
@@ -185,7 +187,9 @@ __global__ void __launch_bounds__(256) frontend_any_kernel(const __grid_constant
     const int nt = (nj - 1) * PS + PK;
     const int ni = nt + K1 - 1;
     const int i0 = p0 * PS * PS;
-    for (int b = blockIdx.y; b < p.B; b += gridDim.y) {
+    const int nwin = p.win_count ? *p.win_count : p.B;
+    for (int wi = blockIdx.y; wi < nwin; wi += gridDim.y) {
+        const int b = p.win_list ? p.win_list[wi] : wi;
         const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * W + i0;
         for (int c = 0; c < C; ++c)
             for (int i = tid; i < ni; i += 256) xs[c * p.xs_stride + padi(i)] = ld_in<Tin>(xb + (int64_t)c * W + i);
@@ -251,8 +255,17 @@ static int launch_variant(const FrontParams &p, int run, int dtype, dim3 grid, s
 int launch_frontend_generic(const Dims &d, const ConvWeights &cw, const void *x, int dtype,
                             int64_t B, float *feats, int64_t sB, int64_t sP, cudaStream_t st,
                             int num_sms, const char **err) {
+    return launch_frontend_generic_listed(d, cw, x, dtype, B, feats, sB, sP, nullptr, nullptr, st, num_sms, err);
+}
+
+// win_list / win_count (device memory, may be null): recompute only the listed windows; the
+// count is read on the device, so an empty list costs one almost-empty launch and no host sync.
+int launch_frontend_generic_listed(const Dims &d, const ConvWeights &cw, const void *x, int dtype,
+                                   int64_t B, float *feats, int64_t sB, int64_t sP, const int *win_list,
+                                   const int *win_count, cudaStream_t st, int num_sms, const char **err) {
     FrontParams p;
     p.x = x; p.feats = feats; p.sB = sB; p.sP = sP; p.B = (int)B; p.d = d; p.cw = cw;
+    p.win_list = win_list; p.win_count = win_count;
     // 508 final positions -> <= 256 thread-runs of 4 pooled outputs in stage 2 (see header).
     const int kTile = 508;
     p.tile_p = d.L < kTile ? d.L : kTile;
@@ -266,6 +279,7 @@ int launch_frontend_generic(const Dims &d, const ConvWeights &cw, const void *x,
     if (smem > 220 * 1024) { *err = "front end: tile does not fit shared memory (in_channels too large)"; return -1; }
     int gy = (2 * num_sms + p.n_tiles - 1) / p.n_tiles;
     if (gy > B) gy = (int)B;
+    if (win_list && gy > 16) gy = 16;          // the exception path: few windows expected
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
     dim3 grid(p.n_tiles, gy);

@@ -56,6 +56,8 @@ struct FrontParams {
     int n_tiles;
     Dims d;
     int xs_stride, a1_stride;   // padded smem row strides (floats)
+    const int *win_list;        // optional: indices of the windows to process (device memory)
+    const int *win_count;       //           and how many (device memory)
     ConvWeights cw;
 };
 
@@ -83,6 +85,10 @@ __host__ __device__ __forceinline__ int padi(int g) { return g + (g >> 5); }
 int launch_frontend_generic(const Dims &d, const ConvWeights &cw, const void *x, int dtype,
                             int64_t B, float *feats, int64_t sB, int64_t sP, cudaStream_t st,
                             int num_sms, const char **err);
+
+int launch_frontend_generic_listed(const Dims &d, const ConvWeights &cw, const void *x, int dtype,
+                                   int64_t B, float *feats, int64_t sB, int64_t sP, const int *win_list,
+                                   const int *win_count, cudaStream_t st, int num_sms, const char **err);
 
 int launch_head(const Dims &d, const HeadWeights &hw, const float *feats, int64_t sB, int64_t sP,
                 int64_t B, const float *age, int64_t n_age, int mode, int apply_sigmoid,

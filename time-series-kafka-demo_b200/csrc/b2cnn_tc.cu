@@ -1,26 +1,497 @@
-// b2cnn_tc.cu -- tcgen05 fast path (placeholder until the kernel lands: reports "unsupported"
-// so every call takes the exact generic path; never a CPU fallback).
+// b2cnn_tc.cu -- tcgen05 / TMEM / TMA front end for bf16 windows (sm_100a).
+//
+// conv1 (bin/models.py:23) is 82 % of the path's FLOPs at the headline shape [4096,3,75000]:
+// 9.0 M MAC per window, which on the FP32 CUDA cores alone costs ~4x the time the HBM roofline
+// allows.  Here it runs on the 5th-gen tensor cores as a banded-Toeplitz GEMM whose M axis is
+// the WINDOW index:
+//
+//   D[w, (s,o)] = sum_{c} sum_{k<16}  X_c[w, 8n+k] * T_c[k, (s,o)],   T_c[k,(s,o)] = w1[o][c][k-s]
+//
+//   * A = X_c: 128 windows x 64 consecutive samples of channel c, brought by ONE 3-D TMA box
+//     {64 samples, 1 channel, 128 windows} into the canonical K-major SWIZZLE_128B layout; the
+//     8-position block n of the tile uses the K=16 slice starting at 16-byte chunk n (descriptor
+//     start address + 16n bytes), so one landed tile feeds 7 blocks = 56 conv1 positions
+//     (tiles advance by 56 samples; the 8 overlapping samples are re-read from L2, not HBM).
+//   * B = T_c: the fp32 conv1 weights expanded to a 16 x 32 band matrix (8 output shifts s x 4
+//     output channels o) and split into 2 or 3 bf16 pieces (hi/mid/lo) so that, the inputs
+//     being exactly bf16, every product is exact and the fp32 accumulation in TMEM carries the
+//     full fp32 weight precision.  One MMA (M=128,N=32,K=16) per (block, channel, piece).
+//   * The one tap that does not fit a 16-sample slice (s=7, k=9 -> sample 8n+16) is added by
+//     the epilogue on the CUDA cores from the same shared-memory tile (12 FMA per block).
+//   * Epilogue: thread == window.  Each thread streams through its window's positions in
+//     order, so pool1 -> tanh -> conv2 -> pool2 -> tanh are register-local sliding windows with
+//     no shuffles, seams or shared-memory exchange; tanh is 1 - 2/(1+2^(2x log2 e)) on
+//     MUFU.EX2 + MUFU.RCP with the bias folded into the exponent FMA; pooling runs BEFORE the
+//     activation (monotone) with FMNMX3.NAN so NaNs propagate exactly like ATen's max_pool1d.
+//   * Zero band entries turn an inf/NaN sample into NaN for its whole 8-position block, a
+//     superset of the reference's NaNs: a window whose features contain a NaN is flagged and
+//     recomputed by the exact generic kernel (b2cnn_generic.cu), still on the GPU.
+//
+// Warp roles per CTA (192 threads, 2 CTAs/SM): warp 0 TMA producer, warp 1 TMEM allocator +
+// single-thread MMA issuer, warps 2-5 epilogue (TMEM lane quadrant = warp % 4).
+// Pipelines: 2 smem stages (full/empty mbarriers), 2 TMEM accumulator stages of 4+3 blocks.
+#include <cuda.h>
+
+#include <cstring>
+#include <vector>
+
 #include "b2cnn_tc.cuh"
 
 namespace b2cnn {
+
 static thread_local const char *g_tc_err = "";
 const char *tc_error() { return g_tc_err; }
-int tc_prepare(TcState &s, const Dims &, const ConvWeights &, const float *, const HeadWeights &, int splits, int, cudaStream_t) {
-    s.splits = splits;
+
+constexpr int kTcM = 128;          // windows per CTA == UMMA M
+constexpr int kTcAdv = 56;         // conv1 positions (= samples) a tile advances
+constexpr int kTcBlocks = 7;       // 8-position blocks per 64-sample tile
+constexpr int kTcABytes = 128 * 128;
+constexpr int kTcBBytes = 32 * 16 * 2;   // one band matrix piece: N=32 x K=16 bf16
+constexpr int kTcMaxC = 4;
+constexpr int kTcThreads = 192;
+constexpr float k2Log2e = 2.8853900817779268f;
+
+struct TcParams {
+    float *feats;
+    int64_t sB, sP;
+    int *nanflag;
+    const uint8_t *bmats;     // [C][SPLITS][1024] bytes, UMMA K-major no-swizzle core-matrix order
+    int B, W, L;
+    int tiles_per_cta, feats_per_cta;
+    float w9[kCMid][kTcMaxC];   // tap k=9 of conv1: w1[o][c][9]
+    float b1s[kCMid];           // conv1 bias * 2 log2 e
+    float w2[kCMid][5];
+    float b2s;                  // conv2 bias * 2 log2 e
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// tanh(m + bias) with bias pre-multiplied by 2 log2 e:  1 - 2 / (1 + 2^(2 log2e (m + bias)))
+__device__ __forceinline__ float tanh_fold(float m, float bias_scaled) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(m, k2Log2e, bias_scaled)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
+// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor bit layout, version 1 = sm_100)
+__device__ __forceinline__ uint64_t desc_sw128_kmajor(uint32_t saddr) {
+    // rows 128 B apart, 8-row groups 1024 B apart, layout_type 2 = SWIZZLE_128B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_none_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=32, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------
+// The kernel (MyCNN5 architecture: K1=10, pool(3,2), K2=5)
+// ------------------------------------------------------------------------------------------
+template <int C, int SPLITS>
+__global__ void __launch_bounds__(kTcThreads, 2)
+tc_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                    // [2 stages][C][16 KB]
+    uint8_t *sBm = smem + 2 * C * kTcABytes;               // [C][SPLITS][1 KB]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sBm + C * SPLITS * kTcBBytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    const uint32_t bar_full = smem_u32(bars + 0), bar_empty = smem_u32(bars + 2);
+    const uint32_t bar_tfull = smem_u32(bars + 4), bar_tempty = smem_u32(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = blockIdx.x * kTcM;
+    const int p0 = blockIdx.y * p.feats_per_cta;
+    const int nfeat = min(p.feats_per_cta, p.L - p0);
+    const int nsteps = (nfeat + 4) / 2;                    // features 2j-3, 2j-2 leave at step j
+    const int ntiles = (nsteps + kTcBlocks - 1) / kTcBlocks;
+    const int T0 = p0 * 4;                                 // first conv1 position == first sample
+
+    // band matrices -> smem (generic proxy), barriers, TMEM
+    for (int i = threadIdx.x; i < C * SPLITS * kTcBBytes / 16; i += kTcThreads)
+        reinterpret_cast<uint4 *>(sBm)[i] = reinterpret_cast<const uint4 *>(p.bmats)[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 4);
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // band matrices visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i & 1, ph = (i >> 1) & 1;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                mbar_expect_tx(bar_full + 8 * s, C * kTcABytes);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    tma_load_3d(smem_u32(sA + (s * C + c) * kTcABytes), &tmap, T0 + kTcAdv * i, c, b0, bar_full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i & 1, ph = (i >> 1) & 1;
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(bar_tempty + 8 * h, (i & 1) ^ 1);
+                    tc_fence_after();
+                    const int nb0 = h ? 4 : 0, nb1 = h ? kTcBlocks : 4;
+                    for (int n = nb0; n < nb1; ++n) {
+                        const uint32_t d = tmem_base + h * 128 + (n - nb0) * 32;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const uint64_t ad = desc_sw128_kmajor(smem_u32(sA + (s * C + c) * kTcABytes) + n * 16);
+#pragma unroll
+                            for (int sp = 0; sp < SPLITS; ++sp) {
+                                const uint64_t bd = desc_none_kmajor(smem_u32(sBm + (c * SPLITS + sp) * kTcBBytes), 128, 256);
+                                umma_bf16(d, ad, bd, kIdesc, (c | sp) != 0);
+                            }
+                        }
+                    }
+                    umma_commit(bar_tfull + 8 * h);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: thread == window =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int b = b0 + row;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t swz = (uint32_t)(row & 7);
+        float pm6[kCMid], pm7[kCMid], ah[4][kCMid], c2c = 0.f, nan_probe = 0.f;
+#pragma unroll
+        for (int o = 0; o < kCMid; ++o) {
+            pm6[o] = 0.f; pm7[o] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ah[i][o] = 0.f;
+        }
+        const bool row_ok = b < p.B;
+        float *fout = p.feats + (int64_t)b * p.sB + (int64_t)p0 * p.sP;
+
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i & 1;
+            mbar_wait(bar_full + 8 * s, (i >> 1) & 1);     // TMA bytes visible to this thread too
+            const uint8_t *tile = sA + (size_t)s * C * kTcABytes + row * 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(bar_tfull + 8 * h, i & 1);
+                tc_fence_after();
+                const int nb0 = h ? 4 : 0, nb1 = h ? kTcBlocks : 4;
+#pragma unroll
+                for (int n = nb0; n < nb1; ++n) {
+                    float D[32];
+                    tmem_ld32(taddr + h * 128 + (n - nb0) * 32, D);
+                    if (n == nb1 - 1) {                    // accumulator stage drained -> MMA may refill it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * h);
+                    }
+                    const int j = i * kTcBlocks + n;       // global step index
+                    // ---- the tap that does not fit the 16-sample slice: previous block's s=7, k=9
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const uint16_t raw = *reinterpret_cast<const uint16_t *>(
+                            tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
+                        const float xv = __uint_as_float((uint32_t)raw << 16);
+#pragma unroll
+                        for (int o = 0; o < kCMid; ++o) pm7[o] = fmaf(p.w9[o][c], xv, pm7[o]);
+                    }
+                    // ---- pool1 (3,2) on pre-activations, then tanh(+bias): a1 positions 4j-1 .. 4j+2
+                    float an[4][kCMid];
+#pragma unroll
+                    for (int o = 0; o < kCMid; ++o) {
+                        an[0][o] = tanh_fold(max3_nan(pm6[o], pm7[o], D[0 * 4 + o]), p.b1s[o]);
+                        an[1][o] = tanh_fold(max3_nan(D[0 * 4 + o], D[1 * 4 + o], D[2 * 4 + o]), p.b1s[o]);
+                        an[2][o] = tanh_fold(max3_nan(D[2 * 4 + o], D[3 * 4 + o], D[4 * 4 + o]), p.b1s[o]);
+                        an[3][o] = tanh_fold(max3_nan(D[4 * 4 + o], D[5 * 4 + o], D[6 * 4 + o]), p.b1s[o]);
+                        pm6[o] = D[6 * 4 + o];
+                        pm7[o] = D[7 * 4 + o];
+                    }
+                    // ---- conv2 (no bias yet): outputs r = 4j-5 .. 4j-2 from a1[r .. r+4]
+                    float c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < kCMid; ++c) {
+                        const float A8[8] = {ah[0][c], ah[1][c], ah[2][c], ah[3][c], an[0][c], an[1][c], an[2][c], an[3][c]};
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) c2[r] = fmaf(p.w2[c][k], A8[r + k], c2[r]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < kCMid; ++c)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) ah[r][c] = an[r][c];
+                    // ---- pool2 (3,2) + tanh(+bias): features 2j-3 and 2j-2
+                    const float f0 = tanh_fold(max3_nan(c2c, c2[0], c2[1]), p.b2s);
+                    const float f1 = tanh_fold(max3_nan(c2[1], c2[2], c2[3]), p.b2s);
+                    c2c = c2[3];
+                    nan_probe = fmaf(f0, 0.f, nan_probe);
+                    nan_probe = fmaf(f1, 0.f, nan_probe);
+                    const int pr0 = 2 * j - 3;
+                    if (row_ok) {
+                        if (pr0 >= 0 && pr0 < nfeat) fout[(int64_t)pr0 * p.sP] = f0;
+                        if (pr0 + 1 >= 0 && pr0 + 1 < nfeat) fout[(int64_t)(pr0 + 1) * p.sP] = f1;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // smem stage fully consumed
+        }
+        if (row_ok && nan_probe != nan_probe) p.nanflag[b] = 1;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+// windows flagged by the tensor-core kernel -> compact index list for the exact re-computation
+__global__ void tc_compact_flags_kernel(int *flags, int B, int *list, int *count) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && flags[b]) {
+        flags[b] = 0;
+        list[atomicAdd(count, 1)] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+static uint16_t bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float bf16_to_f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+static bool arch_ok(const Dims &d) {
+    return d.K1 == 10 && d.K2 == 5 && d.PK == 3 && d.PS == 2 && d.C >= 1 && d.C <= kTcMaxC &&
+           d.act == B2CNN_ACT_TANH && !d.has_affine && (d.W % 8) == 0 && d.L >= 32;
+}
+
+int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *, const HeadWeights &, int splits, int,
+               cudaStream_t st) {
     s.ready = false;
+    s.splits = splits;
+    if (!arch_ok(d)) return 0;                 // not an error: this shape takes the generic path
+    if (!get_encode()) return 0;
+    // band matrices: piece sp of T_c[k][(s,o)] = w1[o][c][k-s], stored as UMMA K-major
+    // no-swizzle core matrices: byte = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2, n = s*4+o
+    std::vector<uint16_t> host((size_t)d.C * splits * 512, 0);
+    for (int c = 0; c < d.C; ++c)
+        for (int sft = 0; sft < 8; ++sft)
+            for (int o = 0; o < kCMid; ++o)
+                for (int k = 0; k < 16; ++k) {
+                    const int tap = k - sft;
+                    if (tap < 0 || tap >= d.K1) continue;
+                    float w = cw.w1[(c * d.K1 + tap) * kCMid + o];
+                    const int n = sft * 4 + o;
+                    const size_t off = (size_t)(n / 8) * 128 + (k / 8) * 64 + (n % 8) * 8 + (k % 8);   // in bf16 units
+                    for (int sp = 0; sp < splits; ++sp) {
+                        const uint16_t piece = bf16_rn(w);
+                        host[((size_t)c * splits + sp) * 512 + off] = piece;
+                        w -= bf16_to_f(piece);
+                    }
+                }
+    if (!s.d_bmats && cudaMalloc(&s.d_bmats, host.size() * 2 + 16) != cudaSuccess) { g_tc_err = "cudaMalloc(band matrices)"; return -1; }
+    if (cudaMemcpyAsync(s.d_bmats, host.data(), host.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { g_tc_err = "upload band matrices"; return -1; }
+    s.ready = true;
     return 0;
 }
-void tc_release(TcState &s) { s.ready = false; }
-bool tc_supported(const TcState &s, const Dims &, int, int64_t, int) { return s.ready; }
-bool tc_can_emit_features(const TcState &) { return false; }
-int64_t tc_workspace_bytes(const TcState &, const Dims &, int64_t) { return 0; }
-int tc_forward(TcState &, const Dims &, const ConvWeights &, const HeadWeights &, const void *, int64_t, const float *, int64_t,
-               int, float *, float *, float *, float *, void *, int, cudaStream_t, const char **err) {
-    *err = "tensor-core path not built";
-    return -1;
+
+void tc_release(TcState &s) {
+    cudaFree(s.d_bmats);
+    s.d_bmats = nullptr;
+    s.ready = false;
 }
-int tc_features(TcState &, const Dims &, const void *, int64_t, float *, int, cudaStream_t, const char **err) {
-    *err = "tensor-core path not built";
-    return -1;
+
+bool tc_supported(const TcState &s, const Dims &d, int dtype, int64_t B, int mode) {
+    (void)mode; (void)B;
+    return s.ready && dtype == B2CNN_DTYPE_BF16 && arch_ok(d);
 }
+bool tc_can_emit_features(const TcState &s) { return s.ready; }
+
+// tc workspace: nan flags [B] + list [B] + count
+int64_t tc_workspace_bytes(const TcState &s, const Dims &, int64_t B) {
+    if (!s.ready) return 0;
+    return ((2 * B + 64) * 4 + 255) / 256 * 256;
+}
+
+static int tiles_per_cta_for(const Dims &d) {
+    // ~515 features per CTA: 37 position ranges x 32 window tiles = 1184 CTAs = 4 waves of 296
+    (void)d;
+    return 37;
+}
+
+static int launch_tc_kernel(const TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B,
+                            float *feats, int64_t sB, int64_t sP, int *nanflag, cudaStream_t st, const char **err) {
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
+    CUtensorMap tm;
+    cuuint64_t gdim[3] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)d.W * 2, (cuuint64_t)d.C * d.W * 2};
+    cuuint32_t box[3] = {64, 1, kTcM};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
+    TcParams p;
+    memset(&p, 0, sizeof p);
+    p.feats = feats; p.sB = sB; p.sP = sP; p.nanflag = nanflag;
+    p.bmats = reinterpret_cast<const uint8_t *>(s.d_bmats);
+    p.B = (int)B; p.W = d.W; p.L = d.L;
+    p.tiles_per_cta = tiles_per_cta_for(d);
+    p.feats_per_cta = 14 * p.tiles_per_cta - 3;
+    for (int o = 0; o < kCMid; ++o) {
+        for (int c = 0; c < d.C; ++c) p.w9[o][c] = cw.w1[(c * d.K1 + 9) * kCMid + o];
+        p.b1s[o] = cw.b1[o] * k2Log2e;
+        for (int k = 0; k < 5; ++k) p.w2[o][k] = cw.w2[o * d.K2 + k];
+    }
+    p.b2s = cw.b2 * k2Log2e;
+    const int n_pr = (d.L + p.feats_per_cta - 1) / p.feats_per_cta;
+    dim3 grid((unsigned)((B + kTcM - 1) / kTcM), n_pr);
+    const size_t smem = (size_t)2 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 256 + 1024;
+#define TC_LAUNCH(CC, SS)                                                                              \
+    if (d.C == CC && s.splits == SS) {                                                                 \
+        cudaError_t e = cudaFuncSetAttribute(tc_frontend_kernel<CC, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }                             \
+        tc_frontend_kernel<CC, SS><<<grid, kTcThreads, smem, st>>>(tm, p);                             \
+    } else
+    TC_LAUNCH(3, 3) TC_LAUNCH(3, 2) TC_LAUNCH(1, 3) TC_LAUNCH(2, 3) TC_LAUNCH(4, 3) TC_LAUNCH(4, 2)
+    { *err = "no tensor-core instantiation for this channel count / split"; return -1; }
+#undef TC_LAUNCH
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    return 1;
+}
+
+// TMA/tcgen05 front end + NaN-flag compaction + exact re-computation of flagged windows.
+// `ws`: 2*B+64 ints of scratch (flags, list, count); pass nullptr to allocate stream-ordered.
+int tc_frontend(TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B, float *feats,
+                int64_t sB, int64_t sP, void *ws, int num_sms, cudaStream_t st, const char **err) {
+    int *flags = reinterpret_cast<int *>(ws);
+    const bool own = flags == nullptr;
+    if (own && cudaMallocAsync(&flags, sizeof(int) * (2 * B + 64), st) != cudaSuccess) { *err = "cudaMallocAsync"; return -1; }
+    int *list = flags + B, *count = list + B;
+    int launches = -1;
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) {
+        *err = "memset flags";
+    } else {
+        int n = launch_tc_kernel(s, d, cw, x, B, feats, sB, sP, flags, st, err);
+        if (n >= 0) {
+            tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
+            int m = launch_frontend_generic_listed(d, cw, x, B2CNN_DTYPE_BF16, B, feats, sB, sP, list, count, st, num_sms, err);
+            if (m >= 0) launches = n + 1 + m;
+        }
+    }
+    if (own) cudaFreeAsync(flags, st);
+    return launches;
+}
+
+int tc_features(TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B, float *feats,
+                int num_sms, cudaStream_t st, const char **err) {
+    // parity-test entry: row-major [B][L] features (uncoalesced stores; not a timed path)
+    return tc_frontend(s, d, cw, x, B, feats, d.L, 1, nullptr, num_sms, st, err);
+}
+
 }  // namespace b2cnn

@@ -19,10 +19,9 @@ bool tc_supported(const TcState &s, const Dims &d, int dtype, int64_t B, int mod
 bool tc_can_emit_features(const TcState &s);
 int64_t tc_workspace_bytes(const TcState &s, const Dims &d, int64_t B);
 // returns number of kernel launches, or <0 with *err set
-int tc_forward(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
-               const float *age, int64_t n_age, int apply_sigmoid, float *out, float *feats, float *partial,
-               float *gates, void *tc_ws, int num_sms, cudaStream_t st, const char **err);
-int tc_features(TcState &s, const Dims &d, const void *x, int64_t B, float *feats, int num_sms, cudaStream_t st,
-                const char **err);
+int tc_frontend(TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B, float *feats,
+                int64_t sB, int64_t sP, void *ws, int num_sms, cudaStream_t st, const char **err);
+int tc_features(TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B, float *feats,
+                int num_sms, cudaStream_t st, const char **err);
 
 }  // namespace b2cnn
