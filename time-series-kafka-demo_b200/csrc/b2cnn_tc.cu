@@ -32,6 +32,7 @@
 // Pipelines: 2 smem stages (full/empty mbarriers), 2 TMEM accumulator stages of 4+3 blocks.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -418,8 +419,9 @@ int64_t tc_workspace_bytes(const TcState &s, const Dims &, int64_t B) {
 }
 
 static int tiles_per_cta_for(const Dims &d) {
-    // ~515 features per CTA: 37 position ranges x 32 window tiles = 1184 CTAs = 4 waves of 296
+    // ~514 features per CTA: 37 position ranges x 32 window tiles = 1184 CTAs = 4 waves of 296
     (void)d;
+    if (const char *e = getenv("B2CNN_TC_TILES")) { const int v = atoi(e); if (v >= 1 && v <= 4096) return v; }
     return 37;
 }
 
@@ -441,7 +443,10 @@ static int launch_tc_kernel(const TcState &s, const Dims &d, const ConvWeights &
     p.bmats = reinterpret_cast<const uint8_t *>(s.d_bmats);
     p.B = (int)B; p.W = d.W; p.L = d.L;
     p.tiles_per_cta = tiles_per_cta_for(d);
-    p.feats_per_cta = 14 * p.tiles_per_cta - 3;
+    // a CTA's stream can emit 14*tiles - 3 features; an EVEN count keeps every range's first
+    // sample (4 * p0 elements) 16-byte aligned for the TMA box start.
+    p.feats_per_cta = 14 * p.tiles_per_cta - 4;
+    if (getenv("B2CNN_TC_ODD_RANGES")) p.feats_per_cta = 14 * p.tiles_per_cta - 3;   // experiment only
     for (int o = 0; o < kCMid; ++o) {
         for (int c = 0; c < d.C; ++c) p.w9[o][c] = cw.w1[(c * d.K1 + 9) * kCMid + o];
         p.b1s[o] = cw.b1[o] * k2Log2e;
