@@ -100,3 +100,31 @@ def test_tc_refuses_unsupported_shapes_instead_of_falling_back():
     _, m = _pair(3, 7504)
     with pytest.raises(RuntimeError, match="tensor"):
         m.predict(torch.zeros(4, 3, 7504, dtype=torch.float32, device=DEV))   # fp32 input
+
+
+@pytest.mark.parametrize("C,W,B,dist", [(3, 7504, 300, "normal"), (3, 7504, 513, "physio"), (1, 2048, 130, "normal"),
+                                        (2, 4000, 64, "normal"), (3, 75000, 9, "normal"), (3, 1528, 5, "normal")])
+def test_tc_unfused_kernels_agree_with_fused(C, W, B, dist):
+    """tc_fused=0: tensor-core front end -> features in HBM -> CUDA-core projection (the first
+    version of the path).  Both variants must meet the oracle and each other."""
+    ref, m = _pair(C, W)
+    x = tskd_b200.synth.make_windows(B, C, W, dist, seed=31, dtype=torch.bfloat16).to(DEV)
+    ages = tskd_b200.synth.make_ages(B, seed=31).to(DEV)
+    fused = m.predict(x, ages).cpu().numpy()
+    n_fused = m.gpu_launches
+    m.set_option("tc_fused", 0)
+    unfused = m.predict(x, ages).cpu().numpy()
+    assert m.last_path == "tensorcore" and m.gpu_launches != n_fused
+    want = O.ref_independent(ref, x.float().cpu(), ages.cpu()).numpy()
+    assert rel_err(fused, want) <= TOL and rel_err(unfused, want) <= TOL
+    assert rel_err(fused, unfused) <= 2e-5
+
+
+def test_tc_fused_prefix_and_permutation_consistency():
+    _, m = _pair(3, 7504)
+    x = tskd_b200.synth.make_windows(700, 3, 7504, "normal", seed=33, dtype=torch.bfloat16).to(DEV)
+    ages = tskd_b200.synth.make_ages(700, seed=33).to(DEV)
+    y = m.predict(x, ages)
+    assert torch.equal(m.predict(x[:300], ages[:300]), y[:300])
+    perm = torch.randperm(700, device=DEV)
+    assert torch.equal(m.predict(x[perm], ages[perm]), y[perm])

@@ -203,7 +203,8 @@ extern "C" int b2cnn_set_weights(b2cnn_handle *h, const float *blob, int64_t n, 
 extern "C" int64_t b2cnn_workspace_bytes(b2cnn_handle *h, int64_t B, int mode) {
     if (!h || B < 1) return -1;
     (void)mode;
-    const int ks = choose_ksplit(B, h->d.L, h->num_sms);
+    int ks = choose_ksplit(B, h->d.L, h->num_sms);
+    if (tc_partial_slices(h->tc) > ks) ks = tc_partial_slices(h->tc);
     int64_t bytes = align_up(B * h->d.L * 4, 256) + align_up((int64_t)ks * B * kGates * 4, 256) + align_up(B * kGates * 4, 256);
     bytes += tc_workspace_bytes(h->tc, h->d, B);
     return bytes;
@@ -218,9 +219,10 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
                           int mode, int apply_sigmoid, float *out, void *ws, int64_t ws_bytes, cudaStream_t st) {
     const Dims &d = h->d;
     const int ks = choose_ksplit(B, d.L, h->num_sms);
+    const int ks_ws = tc_partial_slices(h->tc) > ks ? tc_partial_slices(h->tc) : ks;   // as in b2cnn_workspace_bytes
     char *base = (char *)ws;
     float *feats = (float *)base; base += align_up(B * d.L * 4, 256);
-    float *partial = (float *)base; base += align_up((int64_t)ks * B * kGates * 4, 256);
+    float *partial = (float *)base; base += align_up((int64_t)ks_ws * B * kGates * 4, 256);
     float *gates = (float *)base; base += align_up(B * kGates * 4, 256);
     void *tc_ws = base;
     (void)ws_bytes;
@@ -239,6 +241,19 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
     // are windows, so it writes the transpose [L][B] (coalesced across lanes).
     int64_t sB = d.L, sP = 1;
     int n;
+    if (tc && tc_fused_supported(h->tc, d, dtype)) {
+        // conv + pool + projection fused on the tensor cores: the features never leave the SM
+        n = tc_fused_gates(h->tc, d, h->cw, h->hw, x, B, feats, partial, gates, tc_ws, h->num_sms, st, &err);
+        if (n < 0) return fail(B2CNN_ECUDA, std::string("tensor-core fused kernel: ") + err);
+        launches += n;
+        if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
+        n = launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
+        if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
+        launches += n;
+        if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }
+        h->last_launches = launches; h->last_path = B2CNN_PATH_TENSORCORE;
+        return B2CNN_OK;
+    }
     if (tc) {
         sB = 1; sP = B;
         n = tc_frontend(h->tc, d, h->cw, x, B, feats, sB, sP, tc_ws, h->num_sms, st, &err);
@@ -374,6 +389,7 @@ extern "C" int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value)
         h->opt_path = value;
         return B2CNN_OK;
     }
+    if (!strcmp(key, "tc_fused")) { h->tc.opt_fused = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "profile")) { h->opt_profile = value ? 1 : 0; h->ev_valid = false; return B2CNN_OK; }
     if (!strcmp(key, "tc_splits")) {
         if (value != 2 && value != 3) return fail(B2CNN_EINVAL, "tc_splits must be 2 or 3");

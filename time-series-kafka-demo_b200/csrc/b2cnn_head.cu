@@ -241,21 +241,36 @@ int launch_head(const Dims &d, const HeadWeights &hw, const float *feats, int64_
     dim3 grid((unsigned)((B + kPM - 1) / kPM), ks_eff);
     proj_kernel<<<grid, 256, 0, st>>>(feats, sB, sP, hw.wih0T, partial_ws, (int)B, d.L, kps);
     ++launches;
-    {
-        const int64_t n = B * kGates;
-        reduce_gates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial_ws, ks_eff, B, hw.bih0, hw.bhh0, gates_ws);
-        ++launches;
-    }
-    if (mode == B2CNN_MODE_INDEPENDENT) {
-        head_independent_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(gates_ws, hw, age, n_age, d.age_coef,
-                                                                             apply_sigmoid, out, B);
-    } else {
-        head_sequence_kernel<<<1, 32, 0, st>>>(gates_ws, hw, age, n_age, d.age_coef, apply_sigmoid, out, B);
-    }
-    ++launches;
+    int n = launch_reduce_gates(partial_ws, ks_eff, B, hw, gates_ws, st, err);
+    if (n < 0) return -1;
+    launches += n;
+    n = launch_lstm_head(d, hw, gates_ws, B, age, n_age, mode, apply_sigmoid, out, st, err);
+    if (n < 0) return -1;
+    return launches + n;
+}
+
+// gates[b][g] = (sum over `slices` partial[s][b][g] + b_ih[g]) + b_hh[g], fixed summation order
+int launch_reduce_gates(const float *partial, int slices, int64_t B, const HeadWeights &hw, float *gates,
+                        cudaStream_t st, const char **err) {
+    const int64_t n = B * kGates;
+    reduce_gates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, slices, B, hw.bih0, hw.bhh0, gates);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
-    return launches;
+    return 1;
+}
+
+// LSTM cells + Linear + age scale from layer-0 gate pre-activations (bin/models.py:30-34)
+int launch_lstm_head(const Dims &d, const HeadWeights &hw, const float *gates, int64_t B, const float *age,
+                     int64_t n_age, int mode, int apply_sigmoid, float *out, cudaStream_t st, const char **err) {
+    if (mode == B2CNN_MODE_INDEPENDENT) {
+        head_independent_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(gates, hw, age, n_age, d.age_coef,
+                                                                             apply_sigmoid, out, B);
+    } else {
+        head_sequence_kernel<<<1, 32, 0, st>>>(gates, hw, age, n_age, d.age_coef, apply_sigmoid, out, B);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    return 1;
 }
 
 }  // namespace b2cnn

@@ -95,6 +95,11 @@ int launch_head(const Dims &d, const HeadWeights &hw, const float *feats, int64_
                 float *out, float *gates_ws, float *partial_ws, int ksplit, cudaStream_t st,
                 const char **err);
 
+int launch_reduce_gates(const float *partial, int slices, int64_t B, const HeadWeights &hw, float *gates,
+                        cudaStream_t st, const char **err);
+int launch_lstm_head(const Dims &d, const HeadWeights &hw, const float *gates, int64_t B, const float *age,
+                     int64_t n_age, int mode, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
+
 int choose_ksplit(int64_t B, int L, int num_sms);
 
 void launch_transpose_wih(const float *wih0, float *wih0T, int L, cudaStream_t st);

@@ -37,8 +37,12 @@
 #include <vector>
 
 #include "b2cnn_tc.cuh"
+#include "b2cnn_tc_ptx.cuh"
 
 namespace b2cnn {
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=32 (conv1 bands)
+constexpr uint32_t kIdesc = make_idesc_bf16(128, 32);
 
 static thread_local const char *g_tc_err = "";
 const char *tc_error() { return g_tc_err; }
@@ -50,7 +54,6 @@ constexpr int kTcABytes = 128 * 128;
 constexpr int kTcBBytes = 32 * 16 * 2;   // one band matrix piece: N=32 x K=16 bf16
 constexpr int kTcMaxC = 4;
 constexpr int kTcThreads = 192;
-constexpr float k2Log2e = 2.8853900817779268f;
 
 struct TcParams {
     float *feats;
@@ -64,83 +67,6 @@ struct TcParams {
     float w2[kCMid][5];
     float b2s;                  // conv2 bias * 2 log2 e
 };
-
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float max3_nan(float a, float b, float c) {
-    float r;
-    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
-// tanh(m + bias) with bias pre-multiplied by 2 log2 e:  1 - 2 / (1 + 2^(2 log2e (m + bias)))
-__device__ __forceinline__ float tanh_fold(float m, float bias_scaled) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(m, k2Log2e, bias_scaled)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return fmaf(-2.0f, r, 1.0f);
-}
-
-// UMMA shared-memory descriptors (cute::UMMA::SmemDescriptor bit layout, version 1 = sm_100)
-__device__ __forceinline__ uint64_t desc_sw128_kmajor(uint32_t saddr) {
-    // rows 128 B apart, 8-row groups 1024 B apart, layout_type 2 = SWIZZLE_128B
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ uint64_t desc_none_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=32, M=128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------
 // The kernel (MyCNN5 architecture: K1=10, pool(3,2), K2=5)
@@ -332,6 +258,10 @@ __global__ void tc_compact_flags_kernel(int *flags, int B, int *list, int *count
     }
 }
 
+}  // namespace b2cnn
+#include "b2cnn_tc_fused.cuh"
+namespace b2cnn {
+
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
@@ -369,7 +299,9 @@ static bool arch_ok(const Dims &d) {
            d.act == B2CNN_ACT_TANH && !d.has_affine && (d.W % 8) == 0 && d.L >= 32;
 }
 
-int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *, const HeadWeights &, int splits, int,
+static int tiles_per_cta_for(const Dims &d);
+
+int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_wih0, const HeadWeights &, int splits, int,
                cudaStream_t st) {
     s.ready = false;
     s.splits = splits;
@@ -397,13 +329,31 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *, 
     if (cudaMemcpyAsync(s.d_bmats, host.data(), host.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) { g_tc_err = "upload band matrices"; return -1; }
     s.ready = true;
+    // ---- fused kernel: W_ih_l0 packed per (range, chunk)
+    s.fused_ready = false;
+    s.tiles_per_cta = tiles_per_cta_for(d);
+    s.feats_per_cta = 14 * s.tiles_per_cta - 4;      // even: every range starts 16-byte aligned (TMA)
+    s.chunks_per_cta = (7 * s.tiles_per_cta + 7) / 8;
+    s.n_ranges = (d.L + s.feats_per_cta - 1) / s.feats_per_cta;
+    if (d.C <= 3) {
+        const size_t bytes = (size_t)s.n_ranges * s.chunks_per_cta * kFuWChunkBytes;
+        cudaFree(s.d_wpack); s.d_wpack = nullptr;
+        if (cudaMalloc(&s.d_wpack, bytes) != cudaSuccess) { g_tc_err = "cudaMalloc(packed W_ih)"; return -1; }
+        const int64_t total = (int64_t)s.n_ranges * s.chunks_per_cta * 1024;
+        tc_pack_wih_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_wih0, reinterpret_cast<uint8_t *>(s.d_wpack), d.L,
+                                                                          s.feats_per_cta, s.chunks_per_cta, s.n_ranges);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { g_tc_err = "pack W_ih"; return -1; }
+        s.fused_ready = true;
+    }
     return 0;
 }
 
 void tc_release(TcState &s) {
     cudaFree(s.d_bmats);
+    cudaFree(s.d_wpack);
     s.d_bmats = nullptr;
-    s.ready = false;
+    s.d_wpack = nullptr;
+    s.ready = s.fused_ready = false;
 }
 
 bool tc_supported(const TcState &s, const Dims &d, int dtype, int64_t B, int mode) {
@@ -442,11 +392,10 @@ static int launch_tc_kernel(const TcState &s, const Dims &d, const ConvWeights &
     p.feats = feats; p.sB = sB; p.sP = sP; p.nanflag = nanflag;
     p.bmats = reinterpret_cast<const uint8_t *>(s.d_bmats);
     p.B = (int)B; p.W = d.W; p.L = d.L;
-    p.tiles_per_cta = tiles_per_cta_for(d);
     // a CTA's stream can emit 14*tiles - 3 features; an EVEN count keeps every range's first
-    // sample (4 * p0 elements) 16-byte aligned for the TMA box start.
-    p.feats_per_cta = 14 * p.tiles_per_cta - 4;
-    if (getenv("B2CNN_TC_ODD_RANGES")) p.feats_per_cta = 14 * p.tiles_per_cta - 3;   // experiment only
+    // sample (4 * p0 elements) 16-byte aligned: an unaligned TMA box start faults (measured).
+    p.tiles_per_cta = s.tiles_per_cta;
+    p.feats_per_cta = s.feats_per_cta;
     for (int o = 0; o < kCMid; ++o) {
         for (int c = 0; c < d.C; ++c) p.w9[o][c] = cw.w1[(c * d.K1 + 9) * kCMid + o];
         p.b1s[o] = cw.b1[o] * k2Log2e;
@@ -497,6 +446,76 @@ int tc_features(TcState &s, const Dims &d, const ConvWeights &cw, const void *x,
                 int num_sms, cudaStream_t st, const char **err) {
     // parity-test entry: row-major [B][L] features (uncoalesced stores; not a timed path)
     return tc_frontend(s, d, cw, x, B, feats, d.L, 1, nullptr, num_sms, st, err);
+}
+
+
+bool tc_fused_supported(const TcState &s, const Dims &d, int dtype) {
+    return s.ready && s.fused_ready && s.opt_fused && dtype == B2CNN_DTYPE_BF16 && arch_ok(d) && d.C <= 3;
+}
+int tc_partial_slices(const TcState &s) { return s.fused_ready ? s.n_ranges : 0; }
+
+static int make_tmap(const Dims &d, const void *x, int64_t B, CUtensorMap *tm, const char **err) {
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
+    cuuint64_t gdim[3] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)d.W * 2, (cuuint64_t)d.C * d.W * 2};
+    cuuint32_t box[3] = {64, 1, kTcM};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed"; return -1; }
+    return 0;
+}
+
+// fused front end + projection -> gates[B][64]; flagged (NaN) windows are recomputed exactly.
+int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
+                   float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err) {
+    int *flags = reinterpret_cast<int *>(ws);
+    int *list = flags + B, *count = list + B;
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+    CUtensorMap tm;
+    if (make_tmap(d, x, B, &tm, err) != 0) return -1;
+    TcFusedParams p;
+    memset(&p, 0, sizeof p);
+    p.partial = partial; p.nanflag = flags;
+    p.bmats = reinterpret_cast<const uint8_t *>(s.d_bmats);
+    p.wpack = reinterpret_cast<const uint8_t *>(s.d_wpack);
+    p.B = (int)B; p.W = d.W; p.L = d.L;
+    p.tiles_per_cta = s.tiles_per_cta; p.feats_per_cta = s.feats_per_cta; p.chunks_per_cta = s.chunks_per_cta;
+    for (int o = 0; o < kCMid; ++o) {
+        for (int c = 0; c < d.C; ++c) p.w9[o][c] = cw.w1[(c * d.K1 + 9) * kCMid + o];
+        p.b1s[o] = cw.b1[o] * k2Log2e;
+        for (int k = 0; k < 5; ++k) p.w2[o][k] = cw.w2[o * d.K2 + k];
+    }
+    p.b2s = cw.b2 * k2Log2e;
+    dim3 grid((unsigned)((B + 2 * kTcM - 1) / (2 * kTcM)), s.n_ranges);
+    const size_t smem = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
+                        FuBars::kTotal * 8 + 16;
+#define FU_LAUNCH(CC, SS)                                                                              \
+    if (d.C == CC && s.splits == SS) {                                                                 \
+        cudaError_t e = cudaFuncSetAttribute(tc_fused_kernel<CC, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }                             \
+        tc_fused_kernel<CC, SS><<<grid, kFuThreads, smem, st>>>(tm, p);                                \
+    } else
+    FU_LAUNCH(3, 3) FU_LAUNCH(3, 2) FU_LAUNCH(2, 3) FU_LAUNCH(1, 3)
+    { *err = "no fused instantiation for this channel count / split"; return -1; }
+#undef FU_LAUNCH
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    int launches = 1;
+    tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
+    ++launches;
+    int n = launch_reduce_gates(partial, s.n_ranges, B, hw, gates, st, err);
+    if (n < 0) return -1;
+    launches += n;
+    // the exception path: exact features + projection for flagged windows only
+    n = launch_frontend_generic_listed(d, cw, x, B2CNN_DTYPE_BF16, B, feats, d.L, 1, list, count, st, num_sms, err);
+    if (n < 0) return -1;
+    launches += n;
+    proj_listed_kernel<<<64, 256, 0, st>>>(feats, d.L, 1, hw.wih0T, hw.bih0, hw.bhh0, gates, d.L, list, count);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    return launches + 1;
 }
 
 }  // namespace b2cnn

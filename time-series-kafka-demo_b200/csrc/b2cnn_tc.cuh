@@ -8,7 +8,10 @@ struct TcState {
     bool ready = false;
     int splits = 3;
     void *d_bmats = nullptr;     // Toeplitz-expanded conv1 weights, bf16 pieces (see b2cnn_tc.cu)
-    void *tmap_storage = nullptr;
+    void *d_wpack = nullptr;     // W_ih_l0 packed per (position range, 16-position chunk), 3 bf16 pieces
+    int tiles_per_cta = 37, feats_per_cta = 514, chunks_per_cta = 33, n_ranges = 1;
+    bool fused_ready = false;    // fused conv + projection kernel usable (C <= 3)
+    int64_t opt_fused = 1;
 };
 
 const char *tc_error();
@@ -21,6 +24,11 @@ int64_t tc_workspace_bytes(const TcState &s, const Dims &d, int64_t B);
 // returns number of kernel launches, or <0 with *err set
 int tc_frontend(TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B, float *feats,
                 int64_t sB, int64_t sP, void *ws, int num_sms, cudaStream_t st, const char **err);
+// fused kernel: front end + layer-0 projection; leaves gates[B][64] (biases included).
+bool tc_fused_supported(const TcState &s, const Dims &d, int dtype);
+int tc_partial_slices(const TcState &s);
+int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
+                   float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err);
 int tc_features(TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B, float *feats,
                 int num_sms, cudaStream_t st, const char **err);
 

@@ -1,0 +1,353 @@
+// b2cnn_tc_fused.cuh -- the whole front end AND the LSTM layer-0 input projection in one
+// persistent-style kernel (included by b2cnn_tc.cu).
+//
+// On top of the banded-Toeplitz conv1 of tc_frontend_kernel (see b2cnn_tc.cu) this kernel keeps
+// the features on chip: every epilogue thread (== one window) splits the two features it
+// produces per step into three bf16 pieces and stores them into ITS OWN TMEM lane
+// (tcgen05.st), building the A operand [128 windows x 16 positions] of a second GEMM
+//
+//      gates[w, g] += sum_p  f[w, p] * W_ih_l0[g, p]           (bin/models.py:30, layer 0)
+//
+// issued by the same MMA thread with A in TMEM and B = the packed, bf16-split W_ih chunk that
+// the producer streams with one 1-D bulk TMA per 16 positions.  6 MMAs (M=128, N=64, K=16;
+// piece pairs hh, hm, mh, hl, lh, mm) give fp32-equivalent products; the 64 gate
+// pre-activations accumulate in TMEM across the CTA's whole position range and leave once, as
+// a [range][window][64] partial that reduce_gates_kernel sums in fixed order.  The 307 MB
+// feature round trip through HBM and the CUDA-core projection GEMM disappear.
+//
+// CTA = 2 window tiles (2 x 128 windows) x 1 position range, one CTA per SM, 320 threads:
+//   warp 0      producer: TMA boxes for both window tiles + W_ih chunks
+//   warp 1      TMEM allocator (512 columns) and the single MMA-issuing thread
+//   warps 2-5   epilogue of window tile 0 (TMEM lane quadrant = warp % 4)
+//   warps 6-9   epilogue of window tile 1
+// TMEM columns per window tile (256): conv1 ring 4 x 32 | A pieces 2 x 24 | gates 64.
+#pragma once
+
+namespace b2cnn {
+
+constexpr int kFuThreads = 320;
+constexpr int kFuWChunkBytes = 3 * 64 * 16 * 2;   // 3 pieces x (64 gates x 16 positions) bf16
+constexpr int kFuLag = 4;                         // conv1 blocks the MMA thread runs ahead before a projection chunk
+constexpr uint32_t kIdescProj = make_idesc_bf16(128, 64);
+
+struct TcFusedParams {
+    float *partial;           // [n_ranges][B][64]
+    int *nanflag;             // [B]
+    const uint8_t *bmats;     // conv1 band matrices [C][SPLITS][1 KB]
+    const uint8_t *wpack;     // [n_ranges][chunks_per_cta][kFuWChunkBytes]
+    int B, W, L;
+    int tiles_per_cta, feats_per_cta, chunks_per_cta;
+    float w9[kCMid][kTcMaxC];
+    float b1s[kCMid];
+    float w2[kCMid][5];
+    float b2s;
+};
+
+// barrier indices (uint64_t slots)
+struct FuBars {
+    // per window tile t (stride kPerTile)
+    static constexpr int kFull = 0, kEmpty = 2, kTFull = 4, kTEmpty = 8, kPFull = 12, kPEmpty = 14, kGFull = 16, kPerTile = 17;
+    static constexpr int kWFull = 2 * kPerTile, kWEmpty = kWFull + 2, kTotal = kWEmpty + 2;
+};
+
+template <int C, int SPLITS>
+__global__ void __launch_bounds__(kFuThreads, 1)
+tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcFusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // [2 tiles][2 stages][C][16 KB] | bands | W ring [2][6 KB] | barriers | tmem slot
+    uint8_t *sA = smem;
+    uint8_t *sBm = sA + 2 * 2 * C * kTcABytes;
+    uint8_t *sW = sBm + C * SPLITS * kTcBBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sW + 2 * kFuWChunkBytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + FuBars::kTotal);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int idx) -> uint32_t { return bar0 + 8u * (uint32_t)idx; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_cta = blockIdx.x * 2 * kTcM;
+    const int p0 = blockIdx.y * p.feats_per_cta;
+    const int nfeat = min(p.feats_per_cta, p.L - p0);
+    const int nsteps_needed = (nfeat + 4) / 2;
+    const int ntiles = (nsteps_needed + kTcBlocks - 1) / kTcBlocks;
+    const int J = ntiles * kTcBlocks;                 // steps actually run
+    const int nchunks = (J + 7) / 8;
+    const int T0 = p0 * 4;
+
+    if ((smem_u32(smem) & 1023u) != 0) __trap();      // SWIZZLE_128B tiles need 1 KB alignment
+    for (int i = threadIdx.x; i < C * SPLITS * kTcBBytes / 16; i += kFuThreads)
+        reinterpret_cast<uint4 *>(sBm)[i] = reinterpret_cast<const uint4 *>(p.bmats)[i];
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < 2; ++t) {
+            const int o = t * FuBars::kPerTile;
+            for (int i = 0; i < 2; ++i) { mbar_init(BAR(o + FuBars::kFull + i), 1); mbar_init(BAR(o + FuBars::kEmpty + i), 4); }
+            for (int i = 0; i < 4; ++i) { mbar_init(BAR(o + FuBars::kTFull + i), 1); mbar_init(BAR(o + FuBars::kTEmpty + i), 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(BAR(o + FuBars::kPFull + i), 4); mbar_init(BAR(o + FuBars::kPEmpty + i), 1); }
+            mbar_init(BAR(o + FuBars::kGFull), 1);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FuBars::kWFull + i), 1); mbar_init(BAR(FuBars::kWEmpty + i), 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    auto sA_of = [&](int t, int s, int c) -> uint8_t * { return sA + ((size_t)((t * 2 + s) * C + c)) * kTcABytes; };
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            const uint8_t *wsrc = p.wpack + (size_t)blockIdx.y * p.chunks_per_cta * kFuWChunkBytes;
+            int m_next = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i & 1, ph = (i >> 1) & 1;
+                for (int t = 0; t < 2; ++t) {
+                    const int o = t * FuBars::kPerTile;
+                    mbar_wait(BAR(o + FuBars::kEmpty + s), ph ^ 1);
+                    mbar_expect_tx(BAR(o + FuBars::kFull + s), C * kTcABytes);
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        tma_load_3d(smem_u32(sA_of(t, s, c)), &tmap, T0 + kTcAdv * i, c, b_cta + t * kTcM, BAR(o + FuBars::kFull + s));
+                }
+                while (m_next < nchunks && 8 * m_next <= 7 * i + 14) {
+                    const int u = m_next & 1;
+                    mbar_wait(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
+                    mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
+                    bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m_next * kFuWChunkBytes, kFuWChunkBytes,
+                                 BAR(FuBars::kWFull + u));
+                    ++m_next;
+                }
+            }
+            for (; m_next < nchunks; ++m_next) {
+                const int u = m_next & 1;
+                mbar_wait(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
+                mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
+                bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m_next * kFuWChunkBytes, kFuWChunkBytes,
+                             BAR(FuBars::kWFull + u));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            auto issue_proj = [&](int m) {
+                const int u = m & 1, ph = (m >> 1) & 1;
+                mbar_wait(BAR(FuBars::kWFull + u), ph);
+                for (int t = 0; t < 2; ++t) {
+                    const int o = t * FuBars::kPerTile;
+                    mbar_wait(BAR(o + FuBars::kPFull + u), ph);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + t * 256 + 192;
+                    const uint32_t a0 = tmem_base + t * 256 + 128 + u * 24;
+                    const uint32_t w0 = smem_u32(sW + u * kFuWChunkBytes);
+                    // piece pairs (feature piece, weight piece) with fp + wp <= 2
+                    const int fp[6] = {0, 0, 1, 0, 2, 1}, wp[6] = {0, 1, 0, 2, 0, 1};
+#pragma unroll
+                    for (int e = 0; e < 6; ++e)
+                        umma_bf16_ts(d, a0 + fp[e] * 8, desc_none_kmajor(w0 + wp[e] * 2048, 128, 256), kIdescProj, (m | e) != 0);
+                    umma_commit(BAR(o + FuBars::kPEmpty + u));
+                    umma_commit(BAR(FuBars::kWEmpty + u));
+                }
+            };
+            int m_done = 0;
+            for (int j = 0; j < J; ++j) {
+                const int i = j / kTcBlocks, n = j - i * kTcBlocks, s = i & 1, slot = j & 3;
+                if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done); ++m_done; }
+                for (int t = 0; t < 2; ++t) {
+                    const int o = t * FuBars::kPerTile;
+                    if (n == 0) { mbar_wait(BAR(o + FuBars::kFull + s), (i >> 1) & 1); tc_fence_after(); }
+                    mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + t * 256 + slot * 32;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const uint64_t ad = desc_sw128_kmajor(smem_u32(sA_of(t, s, c)) + n * 16);
+#pragma unroll
+                        for (int sp = 0; sp < SPLITS; ++sp)
+                            umma_bf16(d, ad, desc_none_kmajor(smem_u32(sBm + (c * SPLITS + sp) * kTcBBytes), 128, 256), kIdesc, (c | sp) != 0);
+                    }
+                    umma_commit(BAR(o + FuBars::kTFull + slot));
+                }
+            }
+            for (; m_done < nchunks; ++m_done) issue_proj(m_done);
+            for (int t = 0; t < 2; ++t) umma_commit(BAR(t * FuBars::kPerTile + FuBars::kGFull));
+        }
+    } else {
+        // ===================== epilogue: thread == window =====================
+        const int t = (warp - 2) >> 2;
+        const int o_bar = t * FuBars::kPerTile;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int b = b_cta + t * kTcM + row;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
+        const uint32_t swz = (uint32_t)(row & 7);
+        const bool row_ok = b < p.B;
+        float pm6[kCMid], pm7[kCMid], ah[4][kCMid], c2c = 0.f, nan_probe = 0.f;
+#pragma unroll
+        for (int o = 0; o < kCMid; ++o) {
+            pm6[o] = 0.f; pm7[o] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ah[i][o] = 0.f;
+        }
+        uint32_t Dn[32];
+        // prologue: block 0
+        mbar_wait(BAR(o_bar + FuBars::kTFull + 0), 0);
+        tc_fence_after();
+        tmem_ld32_issue(tlane + 0, Dn);
+
+#pragma unroll 1
+        for (int j = 0; j < J; ++j) {
+            const int i = j / kTcBlocks, n = j - i * kTcBlocks, s = i & 1, slot = j & 3;
+            float D[32];
+            tmem_ld32_wait(Dn);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) D[k] = __uint_as_float(Dn[k]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + slot));
+            if (j + 1 < J) {                               // prefetch the next block's accumulators
+                const int s1 = (j + 1) & 3;
+                mbar_wait(BAR(o_bar + FuBars::kTFull + s1), ((j + 1) >> 2) & 1);
+                tc_fence_after();
+                tmem_ld32_issue(tlane + s1 * 32, Dn);
+            }
+            if (n == 0) mbar_wait(BAR(o_bar + FuBars::kFull + s), (i >> 1) & 1);   // TMA bytes visible for the tap-9 reads
+            const uint8_t *tile = sA_of(t, s, 0) + row * 128;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
+                const float xv = __uint_as_float((uint32_t)raw << 16);
+#pragma unroll
+                for (int o = 0; o < kCMid; ++o) pm7[o] = fmaf(p.w9[o][c], xv, pm7[o]);
+            }
+            if (n == kTcBlocks - 1) {                      // last read of this smem stage
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kEmpty + s));
+            }
+            float an[4][kCMid];
+#pragma unroll
+            for (int o = 0; o < kCMid; ++o) {
+                an[0][o] = tanh_fold(max3_nan(pm6[o], pm7[o], D[0 * 4 + o]), p.b1s[o]);
+                an[1][o] = tanh_fold(max3_nan(D[0 * 4 + o], D[1 * 4 + o], D[2 * 4 + o]), p.b1s[o]);
+                an[2][o] = tanh_fold(max3_nan(D[2 * 4 + o], D[3 * 4 + o], D[4 * 4 + o]), p.b1s[o]);
+                an[3][o] = tanh_fold(max3_nan(D[4 * 4 + o], D[5 * 4 + o], D[6 * 4 + o]), p.b1s[o]);
+                pm6[o] = D[6 * 4 + o];
+                pm7[o] = D[7 * 4 + o];
+            }
+            float c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < kCMid; ++c) {
+                const float A8[8] = {ah[0][c], ah[1][c], ah[2][c], ah[3][c], an[0][c], an[1][c], an[2][c], an[3][c]};
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) c2[r] = fmaf(p.w2[c][k], A8[r + k], c2[r]);
+            }
+#pragma unroll
+            for (int c = 0; c < kCMid; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) ah[r][c] = an[r][c];
+            const float f0 = tanh_fold(max3_nan(c2c, c2[0], c2[1]), p.b2s);
+            const float f1 = tanh_fold(max3_nan(c2[1], c2[2], c2[3]), p.b2s);
+            c2c = c2[3];
+            nan_probe = fmaf(f0, 0.f, nan_probe);
+            nan_probe = fmaf(f1, 0.f, nan_probe);
+            // ---- features -> three bf16 pieces -> this lane's row of the projection A operand
+            const int m = j >> 3, kk = j & 7, u = m & 1;
+            if (kk == 0) {                                 // first store into buffer u for chunk m
+                mbar_wait(BAR(o_bar + FuBars::kPEmpty + u), ((m >> 1) & 1) ^ 1);
+                tc_fence_after();
+            }
+            const uint32_t h = pack_bf16x2(f0, f1);
+            const float r0 = f0 - __uint_as_float(h << 16), r1 = f1 - __uint_as_float(h & 0xffff0000u);
+            const uint32_t md = pack_bf16x2(r0, r1);
+            const float s0 = r0 - __uint_as_float(md << 16), s1v = r1 - __uint_as_float(md & 0xffff0000u);
+            const uint32_t lo = pack_bf16x2(s0, s1v);
+            const uint32_t abuf = tlane + 128 + u * 24 + kk;
+            tmem_st1(abuf, h);
+            tmem_st1(abuf + 8, md);
+            tmem_st1(abuf + 16, lo);
+            if (kk == 7 || j == J - 1) {
+                for (int z = kk + 1; z < 8; ++z) { tmem_st1(abuf - kk + z, 0u); tmem_st1(abuf - kk + z + 8, 0u); tmem_st1(abuf - kk + z + 16, 0u); }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kPFull + u));
+            }
+        }
+        // ---- gate pre-activations of this CTA's position range -> partial[range][window][64]
+        mbar_wait(BAR(o_bar + FuBars::kGFull), 0);
+        tc_fence_after();
+        float *dst = p.partial + ((int64_t)blockIdx.y * p.B + b) * kGates;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t G[32];
+            tmem_ld32_issue(tlane + 192 + half * 32, G);
+            tmem_ld32_wait(G);
+            if (row_ok) {
+#pragma unroll
+                for (int k = 0; k < 32; k += 4)
+                    *reinterpret_cast<uint4 *>(dst + half * 32 + k) = make_uint4(G[k], G[k + 1], G[k + 2], G[k + 3]);
+            }
+        }
+        if (row_ok && nan_probe != nan_probe) p.nanflag[b] = 1;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// W_ih_l0 [64][L] fp32 -> per (range, 16-position chunk) three bf16 pieces in UMMA K-major
+// no-swizzle core-matrix order (byte = (g/8)*256 + (k/8)*128 + (g%8)*16 + (k%8)*2 per piece).
+// Chunk m of a range covers relative features 16m-3 .. 16m+12 (the stream emits 2j-3, 2j-2 at
+// step j); positions outside the range or beyond L get zero weights, which also masks the
+// stream's warm-up / tail garbage.
+__global__ void tc_pack_wih_kernel(const float *__restrict__ wih, uint8_t *__restrict__ out, int L, int feats_per_cta,
+                                   int chunks_per_cta, int n_ranges) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)n_ranges * chunks_per_cta * 1024;
+    if (e >= total) return;
+    const int k = (int)(e & 15), g = (int)((e >> 4) & 63);
+    const int64_t cm = e >> 10;
+    const int m = (int)(cm % chunks_per_cta), pr = (int)(cm / chunks_per_cta);
+    const int prel = 16 * m - 3 + k;
+    const int pos = pr * feats_per_cta + prel;
+    float w = 0.f;
+    if (prel >= 0 && prel < feats_per_cta && pos < L) w = wih[(int64_t)g * L + pos];
+    uint16_t *base = reinterpret_cast<uint16_t *>(out + (size_t)cm * kFuWChunkBytes);
+    const int off = (g / 8) * 128 + (k / 8) * 64 + (g % 8) * 8 + (k % 8);
+#pragma unroll
+    for (int piece = 0; piece < 3; ++piece) {
+        const __nv_bfloat16 hb = __float2bfloat16_rn(w);
+        base[piece * 1024 + off] = __bfloat16_as_ushort(hb);
+        w -= __bfloat162float(hb);
+    }
+}
+
+// exact projection for the (rare) windows the tensor-core kernel flagged: one CTA per listed
+// window, gates[b][g] = (sum_p feats[b][p] * WT[p][g] + b_ih[g]) + b_hh[g]
+__global__ void __launch_bounds__(256)
+proj_listed_kernel(const float *__restrict__ feats, int64_t sB, int64_t sP, const float *__restrict__ WT,
+                   const float *__restrict__ bih, const float *__restrict__ bhh, float *__restrict__ gates, int L,
+                   const int *__restrict__ list, const int *__restrict__ count) {
+    __shared__ float red[4][kGates];
+    const int g = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int n = *count;
+    for (int wi = blockIdx.x; wi < n; wi += gridDim.x) {
+        const int b = list[wi];
+        float acc = 0.f;
+        for (int pp = sl; pp < L; pp += 4) acc = fmaf(feats[(int64_t)b * sB + (int64_t)pp * sP], WT[(int64_t)pp * kGates + g], acc);
+        red[sl][g] = acc;
+        __syncthreads();
+        if (sl == 0) gates[(int64_t)b * kGates + g] = (((red[0][g] + red[1][g]) + (red[2][g] + red[3][g])) + bih[g]) + bhh[g];
+        __syncthreads();
+    }
+}
+
+}  // namespace b2cnn

@@ -149,6 +149,12 @@ class B200MyCNN(nn.Module):
         if self._handle is not None:
             capi.check(capi.load_library().b2cnn_set_option(self._handle, b"path", _PATHS[path]), "b2cnn_set_option")
 
+    def set_option(self, key: str, value: int):
+        """Library options (include/b2cnn.h): e.g. "tc_fused" = 0 keeps the tensor-core front
+        end and the projection as separate kernels."""
+        lib, h = self._ensure_handle()
+        capi.check(lib.b2cnn_set_option(h, key.encode(), int(value)), "b2cnn_set_option")
+
     def set_profile(self, on: bool = True):
         """Record CUDA events around the stages of every forward (bench.py's roofline figure)."""
         lib, h = self._ensure_handle()
