@@ -51,41 +51,73 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks
+    line), through NVML in a background thread: the timed region is only tens of milliseconds,
+    too short for an `nvidia-smi -lms` child process to produce a sample."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.run, self.thread, self.h = index, [], False, None, None
+        self.t_begin = self.t_end = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
+
+    def _loop(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+        if self.h is None:
+            return
+        self.run = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.run = False
+        self.thread.join(timeout=2)
+        nv = self.nv
+        rows = [r for r in self.rows if self.t_begin is not None and self.t_begin <= r[0] <= self.t_end]
+        where = "timed region"
+        if len(rows) < 3:          # region shorter than a few NVML polls: include the warm-up just before it
+            rows, where = self.rows, "warm-up + timed region"
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        reasons = sorted({n for r in rows for bit, n in names.items() if r[2] & bit})
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm, "samples": len(sm),
+                "power_w_max": max((r[3] for r in rows), default=None), "window": where, "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------------
@@ -189,15 +221,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(args.warmup):
         y = model.predict(x, ages)
     barrier()
     launches_per_step = model.gpu_launches
     path = model.last_path
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.mark_begin()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     ev[0].record()
@@ -205,6 +239,8 @@ def main():
         y = model.predict(x, ages)
         ev[s + 1].record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     total_ms = ev[0].elapsed_time(ev[args.steps])
     # the dominant kernel's own duration: events the library recorded around it on the same
     # stream inside the timed region (last step's value; steps are identical)

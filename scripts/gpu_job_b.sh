@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/b_build.log 2>&1
-timeout 900 python -m pytest tests/test_gpu_tc.py -q -x > gpurun_out/b_tc.log 2>&1; rc=$?; echo "tc pytest rc=$rc" >> gpurun_out/b_tc.log
+timeout -k 10 300 python -m pytest tests/test_gpu_tc.py -q -x > gpurun_out/b_tc.log 2>&1; rc=$?; echo "tc pytest rc=$rc" >> gpurun_out/b_tc.log
 tail -40 gpurun_out/b_tc.log
 if [ $rc -ne 0 ]; then
   timeout 600 python scripts/tc_diag.py > gpurun_out/b_diag.log 2>&1; cat gpurun_out/b_diag.log | tail -40

@@ -113,7 +113,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     for (int c = 0; c < C; ++c)
                         tma_load_3d(smem_u32(sA_of(t, s, c)), &tmap, T0 + kTcAdv * i, c, b_cta + t * kTcM, BAR(o + FuBars::kFull + s));
                 }
-                while (m_next < nchunks && 8 * m_next <= 7 * i + 14) {
+                while (m_next < nchunks && 8 * m_next <= 7 * i + 15 - kFuLag) {   // never wait on a chunk whose consumer needs a tile not issued yet
                     const int u = m_next & 1;
                     mbar_wait(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
                     mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
