@@ -126,31 +126,35 @@ tc_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            for (int i = 0; i < ntiles; ++i) {
-                const int s = i & 1, ph = (i >> 1) & 1;
-                mbar_wait(bar_full + 8 * s, ph);
-                tc_fence_after();
+        // ===================== MMA issuer =====================
+        // whole warp runs the loop (warp-uniform descriptor arithmetic); one elected lane issues
+        const uint64_t a_base = desc_sw128_kmajor(smem_u32(sA));
+        const uint64_t b_base = desc_none_kmajor(smem_u32(sBm), 128, 256);
+        const uint32_t a_lo0 = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
+        const uint32_t b_lo0 = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i & 1, ph = (i >> 1) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    mbar_wait(bar_tempty + 8 * h, (i & 1) ^ 1);
-                    tc_fence_after();
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(bar_tempty + 8 * h, (i & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
                     const int nb0 = h ? 4 : 0, nb1 = h ? kTcBlocks : 4;
                     for (int n = nb0; n < nb1; ++n) {
                         const uint32_t d = tmem_base + h * 128 + (n - nb0) * 32;
+                        const uint32_t a_s = a_lo0 + (uint32_t)(s * C) * (kTcABytes >> 4) + n;
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const uint64_t ad = desc_sw128_kmajor(smem_u32(sA + (s * C + c) * kTcABytes) + n * 16);
+                        for (int c = 0; c < C; ++c)
 #pragma unroll
-                            for (int sp = 0; sp < SPLITS; ++sp) {
-                                const uint64_t bd = desc_none_kmajor(smem_u32(sBm + (c * SPLITS + sp) * kTcBBytes), 128, 256);
-                                umma_bf16(d, ad, bd, kIdesc, (c | sp) != 0);
-                            }
-                        }
+                            for (int sp = 0; sp < SPLITS; ++sp)
+                                umma_ss(d, a_s + c * (kTcABytes >> 4), a_hi, b_lo0 + (c * SPLITS + sp) * (kTcBBytes >> 4), b_hi, kIdesc,
+                                        (c | sp) != 0);
                     }
                     umma_commit(bar_tfull + 8 * h);
                 }
+                __syncwarp();
             }
         }
     } else {

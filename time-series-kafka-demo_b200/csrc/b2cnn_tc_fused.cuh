@@ -22,6 +22,7 @@
 //   warps 6-9   epilogue of window tile 1
 // TMEM columns per window tile (256): conv1 ring 4 x 32 | A pieces 2 x 24 | gates 64.
 #pragma once
+#include <type_traits>
 
 namespace b2cnn {
 
@@ -132,51 +133,75 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            auto issue_proj = [&](int m) {
-                const int u = m & 1, ph = (m >> 1) & 1;
-                mbar_wait(BAR(FuBars::kWFull + u), ph);
-                for (int t = 0; t < 2; ++t) {
-                    const int o = t * FuBars::kPerTile;
-                    mbar_wait(BAR(o + FuBars::kPFull + u), ph);
-                    tc_fence_after();
+        // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic); one
+        // elected lane issues the tcgen05 instructions.  Descriptors are base + small offsets.
+        const uint64_t a_base = desc_sw128_kmajor(smem_u32(sA));
+        const uint64_t b_base = desc_none_kmajor(smem_u32(sBm), 128, 256);
+        const uint64_t w_base = desc_none_kmajor(smem_u32(sW), 128, 256);
+        const uint32_t a_lo0 = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
+        const uint32_t b_lo0 = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
+        const uint32_t w_lo0 = (uint32_t)w_base, w_hi = (uint32_t)(w_base >> 32);
+        auto issue_proj = [&](int m) {
+            const int u = m & 1, ph = (m >> 1) & 1;
+            mbar_wait(BAR(FuBars::kWFull + u), ph);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int o = t * FuBars::kPerTile;
+                mbar_wait(BAR(o + FuBars::kPFull + u), ph);
+                tc_fence_after();
+                if (elect_one()) {
                     const uint32_t d = tmem_base + t * 256 + 192;
                     const uint32_t a0 = tmem_base + t * 256 + 128 + u * 24;
-                    const uint32_t w0 = smem_u32(sW + u * kFuWChunkBytes);
-                    // piece pairs (feature piece, weight piece) with fp + wp <= 2
-                    const int fp[6] = {0, 0, 1, 0, 2, 1}, wp[6] = {0, 1, 0, 2, 0, 1};
-#pragma unroll
-                    for (int e = 0; e < 6; ++e)
-                        umma_bf16_ts(d, a0 + fp[e] * 8, desc_none_kmajor(w0 + wp[e] * 2048, 128, 256), kIdescProj, (m | e) != 0);
+                    const uint32_t w0 = w_lo0 + u * (kFuWChunkBytes >> 4);
+                    // piece pairs (feature piece, weight piece) with fp + wp <= 2: hh hm mh hl lh mm
+                    umma_ts(d, a0 + 0, w0 + 0 * 128, w_hi, kIdescProj, m != 0);
+                    umma_ts(d, a0 + 0, w0 + 1 * 128, w_hi, kIdescProj, 1);
+                    umma_ts(d, a0 + 8, w0 + 0 * 128, w_hi, kIdescProj, 1);
+                    umma_ts(d, a0 + 0, w0 + 2 * 128, w_hi, kIdescProj, 1);
+                    umma_ts(d, a0 + 16, w0 + 0 * 128, w_hi, kIdescProj, 1);
+                    umma_ts(d, a0 + 8, w0 + 1 * 128, w_hi, kIdescProj, 1);
                     umma_commit(BAR(o + FuBars::kPEmpty + u));
                     umma_commit(BAR(FuBars::kWEmpty + u));
                 }
-            };
-            int m_done = 0;
-            for (int j = 0; j < J; ++j) {
-                const int i = j / kTcBlocks, n = j - i * kTcBlocks, s = i & 1, slot = j & 3;
-                if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done); ++m_done; }
-                for (int t = 0; t < 2; ++t) {
-                    const int o = t * FuBars::kPerTile;
-                    if (n == 0) { mbar_wait(BAR(o + FuBars::kFull + s), (i >> 1) & 1); tc_fence_after(); }
-                    mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d = tmem_base + t * 256 + slot * 32;
+                __syncwarp();
+            }
+        };
+        int m_done = 0, n = 0, i = 0;
+        for (int j = 0; j < J; ++j) {
+            const int s = i & 1, slot = j & 3;
+            if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done); ++m_done; }
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const uint64_t ad = desc_sw128_kmajor(smem_u32(sA_of(t, s, c)) + n * 16);
+            for (int t = 0; t < 2; ++t) {
+                const int o = t * FuBars::kPerTile;
+                if (n == 0) mbar_wait(BAR(o + FuBars::kFull + s), (i >> 1) & 1);
+                mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d = tmem_base + t * 256 + slot * 32;
+                    const uint32_t a_ts = a_lo0 + (uint32_t)((t * 2 + s) * C) * (kTcABytes >> 4) + n;
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
 #pragma unroll
                         for (int sp = 0; sp < SPLITS; ++sp)
-                            umma_bf16(d, ad, desc_none_kmajor(smem_u32(sBm + (c * SPLITS + sp) * kTcBBytes), 128, 256), kIdesc, (c | sp) != 0);
-                    }
+                            umma_ss(d, a_ts + c * (kTcABytes >> 4), a_hi, b_lo0 + (c * SPLITS + sp) * (kTcBBytes >> 4), b_hi, kIdesc,
+                                    (c | sp) != 0);
                     umma_commit(BAR(o + FuBars::kTFull + slot));
                 }
+                __syncwarp();
             }
-            for (; m_done < nchunks; ++m_done) issue_proj(m_done);
+            if (++n == kTcBlocks) { n = 0; ++i; }
+        }
+        for (; m_done < nchunks; ++m_done) issue_proj(m_done);
+        if (elect_one()) {
             for (int t = 0; t < 2; ++t) umma_commit(BAR(t * FuBars::kPerTile + FuBars::kGFull));
         }
+        __syncwarp();
     } else {
         // ===================== epilogue: thread == window =====================
+        // Software-pipelined by one step: iteration jj runs stage A of block jj (TMEM -> pool1 ->
+        // tanh) and stage B of step jj-1 (conv2 -> pool2 -> tanh -> bf16 pieces -> TMEM).  The two
+        // stages touch disjoint registers, so their MUFU / FMA chains interleave in one basic block;
+        // all barrier traffic sits at the top and bottom of the iteration.
         const int t = (warp - 2) >> 2;
         const int o_bar = t * FuBars::kPerTile;
         const int q = warp & 3;
@@ -185,99 +210,131 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
         const uint32_t swz = (uint32_t)(row & 7);
         const bool row_ok = b < p.B;
-        float pm6[kCMid], pm7[kCMid], ah[4][kCMid], c2c = 0.f, nan_probe = 0.f;
+        float pm6[kCMid], pm7[kCMid], ah[4][kCMid], ap[4][kCMid], c2c = 0.f, nan_probe = 0.f;
 #pragma unroll
         for (int o = 0; o < kCMid; ++o) {
             pm6[o] = 0.f; pm7[o] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) ah[i][o] = 0.f;
+            for (int i = 0; i < 4; ++i) { ah[i][o] = 0.f; ap[i][o] = 0.f; }
         }
         uint32_t Dn[32];
-        // prologue: block 0
         mbar_wait(BAR(o_bar + FuBars::kTFull + 0), 0);
         tc_fence_after();
         tmem_ld32_issue(tlane + 0, Dn);
+        int n = 0, ti = 0;                                  // block-in-tile and tile index of block jj
 
-#pragma unroll 1
-        for (int j = 0; j < J; ++j) {
-            const int i = j / kTcBlocks, n = j - i * kTcBlocks, s = i & 1, slot = j & 3;
+        auto iteration = [&](int jj, auto doA_, auto doB_) {
+            constexpr bool doA = decltype(doA_)::value, doB = decltype(doB_)::value;
+            const int s = ti & 1;
+            const int jb = jj - 1, m = jb >> 3, kk = jb & 7, u = m & 1;
             float D[32];
-            tmem_ld32_wait(Dn);
+            // ---------------- top: barriers ----------------
+            if constexpr (doA) {
+                tmem_ld32_wait(Dn);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) D[k] = __uint_as_float(Dn[k]);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + slot));
-            if (j + 1 < J) {                               // prefetch the next block's accumulators
-                const int s1 = (j + 1) & 3;
-                mbar_wait(BAR(o_bar + FuBars::kTFull + s1), ((j + 1) >> 2) & 1);
-                tc_fence_after();
-                tmem_ld32_issue(tlane + s1 * 32, Dn);
-            }
-            if (n == 0) mbar_wait(BAR(o_bar + FuBars::kFull + s), (i >> 1) & 1);   // TMA bytes visible for the tap-9 reads
-            const uint8_t *tile = sA_of(t, s, 0) + row * 128;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
-                const float xv = __uint_as_float((uint32_t)raw << 16);
-#pragma unroll
-                for (int o = 0; o < kCMid; ++o) pm7[o] = fmaf(p.w9[o][c], xv, pm7[o]);
-            }
-            if (n == kTcBlocks - 1) {                      // last read of this smem stage
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kEmpty + s));
-            }
-            float an[4][kCMid];
-#pragma unroll
-            for (int o = 0; o < kCMid; ++o) {
-                an[0][o] = tanh_fold(max3_nan(pm6[o], pm7[o], D[0 * 4 + o]), p.b1s[o]);
-                an[1][o] = tanh_fold(max3_nan(D[0 * 4 + o], D[1 * 4 + o], D[2 * 4 + o]), p.b1s[o]);
-                an[2][o] = tanh_fold(max3_nan(D[2 * 4 + o], D[3 * 4 + o], D[4 * 4 + o]), p.b1s[o]);
-                an[3][o] = tanh_fold(max3_nan(D[4 * 4 + o], D[5 * 4 + o], D[6 * 4 + o]), p.b1s[o]);
-                pm6[o] = D[6 * 4 + o];
-                pm7[o] = D[7 * 4 + o];
-            }
-            float c2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < kCMid; ++c) {
-                const float A8[8] = {ah[0][c], ah[1][c], ah[2][c], ah[3][c], an[0][c], an[1][c], an[2][c], an[3][c]};
-#pragma unroll
-                for (int k = 0; k < 5; ++k)
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) c2[r] = fmaf(p.w2[c][k], A8[r + k], c2[r]);
-            }
-#pragma unroll
-            for (int c = 0; c < kCMid; ++c)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) ah[r][c] = an[r][c];
-            const float f0 = tanh_fold(max3_nan(c2c, c2[0], c2[1]), p.b2s);
-            const float f1 = tanh_fold(max3_nan(c2[1], c2[2], c2[3]), p.b2s);
-            c2c = c2[3];
-            nan_probe = fmaf(f0, 0.f, nan_probe);
-            nan_probe = fmaf(f1, 0.f, nan_probe);
-            // ---- features -> three bf16 pieces -> this lane's row of the projection A operand
-            const int m = j >> 3, kk = j & 7, u = m & 1;
-            if (kk == 0) {                                 // first store into buffer u for chunk m
-                mbar_wait(BAR(o_bar + FuBars::kPEmpty + u), ((m >> 1) & 1) ^ 1);
-                tc_fence_after();
-            }
-            const uint32_t h = pack_bf16x2(f0, f1);
-            const float r0 = f0 - __uint_as_float(h << 16), r1 = f1 - __uint_as_float(h & 0xffff0000u);
-            const uint32_t md = pack_bf16x2(r0, r1);
-            const float s0 = r0 - __uint_as_float(md << 16), s1v = r1 - __uint_as_float(md & 0xffff0000u);
-            const uint32_t lo = pack_bf16x2(s0, s1v);
-            const uint32_t abuf = tlane + 128 + u * 24 + kk;
-            tmem_st1(abuf, h);
-            tmem_st1(abuf + 8, md);
-            tmem_st1(abuf + 16, lo);
-            if (kk == 7 || j == J - 1) {
-                for (int z = kk + 1; z < 8; ++z) { tmem_st1(abuf - kk + z, 0u); tmem_st1(abuf - kk + z + 8, 0u); tmem_st1(abuf - kk + z + 16, 0u); }
-                tmem_st_wait();
+                for (int k = 0; k < 32; ++k) D[k] = __uint_as_float(Dn[k]);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kPFull + u));
+                if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + (jj & 3)));
+                if (jj + 1 < J) {                           // prefetch the next block's accumulators
+                    const int s1 = (jj + 1) & 3;
+                    mbar_wait(BAR(o_bar + FuBars::kTFull + s1), ((jj + 1) >> 2) & 1);
+                    tc_fence_after();
+                    tmem_ld32_issue(tlane + s1 * 32, Dn);
+                }
+                if (n == 0) mbar_wait(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1);   // TMA bytes visible for the tap-9 reads
             }
-        }
+            if constexpr (doB) {
+                if (kk == 0) {                              // first store of chunk m into A buffer u
+                    mbar_wait(BAR(o_bar + FuBars::kPEmpty + u), ((m >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                }
+            }
+            // ---------------- middle: straight-line math ----------------
+            float an[4][kCMid];
+            if constexpr (doA) {
+                const uint8_t *tile = sA_of(t, s, 0) + row * 128;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
+                    const float xv = __uint_as_float((uint32_t)raw << 16);
+#pragma unroll
+                    for (int o = 0; o < kCMid; ++o) pm7[o] = fmaf(p.w9[o][c], xv, pm7[o]);
+                }
+#pragma unroll
+                for (int o = 0; o < kCMid; ++o) {
+                    an[0][o] = tanh_fold(max3_nan(pm6[o], pm7[o], D[0 * 4 + o]), p.b1s[o]);
+                    an[1][o] = tanh_fold(max3_nan(D[0 * 4 + o], D[1 * 4 + o], D[2 * 4 + o]), p.b1s[o]);
+                    an[2][o] = tanh_fold(max3_nan(D[2 * 4 + o], D[3 * 4 + o], D[4 * 4 + o]), p.b1s[o]);
+                    an[3][o] = tanh_fold(max3_nan(D[4 * 4 + o], D[5 * 4 + o], D[6 * 4 + o]), p.b1s[o]);
+                    pm6[o] = D[6 * 4 + o];
+                    pm7[o] = D[7 * 4 + o];
+                }
+            }
+            if constexpr (doB) {
+                float c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < kCMid; ++c) {
+                    const float A8[8] = {ah[0][c], ah[1][c], ah[2][c], ah[3][c], ap[0][c], ap[1][c], ap[2][c], ap[3][c]};
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) c2[r] = fmaf(p.w2[c][k], A8[r + k], c2[r]);
+                }
+                const float f0 = tanh_fold(max3_nan(c2c, c2[0], c2[1]), p.b2s);   // feature 2*jb-3
+                const float f1 = tanh_fold(max3_nan(c2[1], c2[2], c2[3]), p.b2s);  // feature 2*jb-2
+                c2c = c2[3];
+                nan_probe = fmaf(f0, 0.f, nan_probe);
+                nan_probe = fmaf(f1, 0.f, nan_probe);
+                // three bf16 pieces of (f0, f1) -> column kk of this lane's row of the A operand
+                const uint32_t h = pack_bf16x2(f0, f1);
+                const float r0 = f0 - __uint_as_float(h << 16), r1 = f1 - __uint_as_float(h & 0xffff0000u);
+                const uint32_t md = pack_bf16x2(r0, r1);
+                const float s0 = r0 - __uint_as_float(md << 16), s1v = r1 - __uint_as_float(md & 0xffff0000u);
+                const uint32_t lo = pack_bf16x2(s0, s1v);
+                const uint32_t abuf = tlane + 128 + u * 24 + kk;
+                tmem_st1(abuf, h);
+                tmem_st1(abuf + 8, md);
+                tmem_st1(abuf + 16, lo);
+#pragma unroll
+                for (int c = 0; c < kCMid; ++c)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) ah[r][c] = ap[r][c];
+            }
+            if constexpr (doA) {
+#pragma unroll
+                for (int c = 0; c < kCMid; ++c)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) ap[r][c] = an[r][c];
+            }
+            // ---------------- bottom: arrivals ----------------
+            if constexpr (doA) {
+                if (n == kTcBlocks - 1) {                  // last read of this smem stage
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kEmpty + s));
+                    n = 0; ++ti;
+                } else {
+                    ++n;
+                }
+            }
+            if constexpr (doB) {
+                if (kk == 7 || jb == J - 1) {
+                    const uint32_t abase = tlane + 128 + u * 24;
+                    for (int z = kk + 1; z < 8; ++z) { tmem_st1(abase + z, 0u); tmem_st1(abase + z + 8, 0u); tmem_st1(abase + z + 16, 0u); }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kPFull + u));
+                }
+            }
+        };
+        using T_ = std::integral_constant<bool, true>;
+        using F_ = std::integral_constant<bool, false>;
+        iteration(0, T_{}, F_{});
+#pragma unroll 1
+        for (int jj = 1; jj < J; ++jj) iteration(jj, T_{}, T_{});
+        iteration(J, F_{}, T_{});
+
         // ---- gate pre-activations of this CTA's position range -> partial[range][window][64]
         mbar_wait(BAR(o_bar + FuBars::kGFull), 0);
         tc_fence_after();

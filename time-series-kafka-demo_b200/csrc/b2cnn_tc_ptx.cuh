@@ -126,6 +126,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
     return r;
 }
+// one lane of a converged warp (the rest of the warp stays warp-uniform, so descriptor
+// arithmetic can live in the uniform datapath instead of being moved there per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+// descriptors passed as (lo, hi) halves: the hi half is a per-operand constant
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b64 da, db;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n setp.ne.b32 p, %6, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b64 db;\n mov.b64 db, {%2, %3};\n setp.ne.b32 p, %5, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
