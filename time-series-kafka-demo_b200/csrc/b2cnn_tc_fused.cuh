@@ -15,18 +15,20 @@
 // a [range][window][64] partial that reduce_gates_kernel sums in fixed order.  The 307 MB
 // feature round trip through HBM and the CUDA-core projection GEMM disappear.
 //
-// CTA = 2 window tiles (2 x 128 windows) x 1 position range, one CTA per SM, 320 threads:
+// CTA = 2 window tiles (2 x 128 windows) x 1 position range, one CTA per SM, 384 threads, one
+// control warp + two epilogue warps on every SM sub-partition (warp % 4):
 //   warp 0      producer: TMA boxes for both window tiles + W_ih chunks
-//   warp 1      TMEM allocator (512 columns) and the single MMA-issuing thread
-//   warps 2-5   epilogue of window tile 0 (TMEM lane quadrant = warp % 4)
-//   warps 6-9   epilogue of window tile 1
+//   warp 1 / 2  MMA issuer of window tile 0 / 1 (conv1 bands + projection), one elected lane
+//   warp 3      TMEM allocator (512 columns)
+//   warps 4-7   epilogue of window tile 0 (TMEM lane quadrant = warp % 4)
+//   warps 8-11  epilogue of window tile 1
 // TMEM columns per window tile (256): conv1 ring 4 x 32 | A pieces 2 x 24 | gates 64.
 #pragma once
 #include <type_traits>
 
 namespace b2cnn {
 
-constexpr int kFuThreads = 320;
+constexpr int kFuThreads = 384;
 constexpr int kFuWChunkBytes = 3 * 64 * 16 * 2;   // 3 pieces x (64 gates x 16 positions) bf16
 constexpr int kFuLag = 4;                         // conv1 blocks the MMA thread runs ahead before a projection chunk
 constexpr uint32_t kIdescProj = make_idesc_bf16(128, 64);
@@ -64,7 +66,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int idx) -> uint32_t { return bar0 + 8u * (uint32_t)idx; };
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const int b_cta = blockIdx.x * 2 * kTcM;
     const int p0 = blockIdx.y * p.feats_per_cta;
     const int nfeat = min(p.feats_per_cta, p.L - p0);
@@ -88,7 +91,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(FuBars::kWFull + i), 1); mbar_init(BAR(FuBars::kWEmpty + i), 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -108,7 +111,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 const int s = i & 1, ph = (i >> 1) & 1;
                 for (int t = 0; t < 2; ++t) {
                     const int o = t * FuBars::kPerTile;
-                    mbar_wait(BAR(o + FuBars::kEmpty + s), ph ^ 1);
+                    mbar_wait_parked(BAR(o + FuBars::kEmpty + s), ph ^ 1);
                     mbar_expect_tx(BAR(o + FuBars::kFull + s), C * kTcABytes);
 #pragma unroll
                     for (int c = 0; c < C; ++c)
@@ -116,7 +119,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
                 while (m_next < nchunks && 8 * m_next <= 7 * i + 15 - kFuLag) {   // never wait on a chunk whose consumer needs a tile not issued yet
                     const int u = m_next & 1;
-                    mbar_wait(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
+                    mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
                     mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
                     bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m_next * kFuWChunkBytes, kFuWChunkBytes,
                                  BAR(FuBars::kWFull + u));
@@ -125,84 +128,79 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             }
             for (; m_next < nchunks; ++m_next) {
                 const int u = m_next & 1;
-                mbar_wait(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
+                mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
                 mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
                 bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m_next * kFuWChunkBytes, kFuWChunkBytes,
                              BAR(FuBars::kWFull + u));
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 2) {
+        // ===================== MMA issuer of window tile t =====================
         // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic); one
         // elected lane issues the tcgen05 instructions.  Descriptors are base + small offsets.
-        const uint64_t a_base = desc_sw128_kmajor(smem_u32(sA));
+        const int t = warp - 1;
+        const int o = t * FuBars::kPerTile;
+        const uint64_t a_base = desc_sw128_kmajor(smem_u32(sA_of(t, 0, 0)));
         const uint64_t b_base = desc_none_kmajor(smem_u32(sBm), 128, 256);
         const uint64_t w_base = desc_none_kmajor(smem_u32(sW), 128, 256);
         const uint32_t a_lo0 = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
         const uint32_t b_lo0 = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
         const uint32_t w_lo0 = (uint32_t)w_base, w_hi = (uint32_t)(w_base >> 32);
+        const uint32_t tcol = tmem_base + t * 256;
         auto issue_proj = [&](int m) {
             const int u = m & 1, ph = (m >> 1) & 1;
-            mbar_wait(BAR(FuBars::kWFull + u), ph);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int o = t * FuBars::kPerTile;
-                mbar_wait(BAR(o + FuBars::kPFull + u), ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d = tmem_base + t * 256 + 192;
-                    const uint32_t a0 = tmem_base + t * 256 + 128 + u * 24;
-                    const uint32_t w0 = w_lo0 + u * (kFuWChunkBytes >> 4);
-                    // piece pairs (feature piece, weight piece) with fp + wp <= 2: hh hm mh hl lh mm
-                    umma_ts(d, a0 + 0, w0 + 0 * 128, w_hi, kIdescProj, m != 0);
-                    umma_ts(d, a0 + 0, w0 + 1 * 128, w_hi, kIdescProj, 1);
-                    umma_ts(d, a0 + 8, w0 + 0 * 128, w_hi, kIdescProj, 1);
-                    umma_ts(d, a0 + 0, w0 + 2 * 128, w_hi, kIdescProj, 1);
-                    umma_ts(d, a0 + 16, w0 + 0 * 128, w_hi, kIdescProj, 1);
-                    umma_ts(d, a0 + 8, w0 + 1 * 128, w_hi, kIdescProj, 1);
-                    umma_commit(BAR(o + FuBars::kPEmpty + u));
-                    umma_commit(BAR(FuBars::kWEmpty + u));
-                }
-                __syncwarp();
+            mbar_wait_parked(BAR(FuBars::kWFull + u), ph);
+            mbar_wait_parked(BAR(o + FuBars::kPFull + u), ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tcol + 192;
+                const uint32_t a0 = tcol + 128 + u * 24;
+                const uint32_t w0 = w_lo0 + u * (kFuWChunkBytes >> 4);
+                // piece pairs (feature piece, weight piece) with fp + wp <= 2: hh hm mh hl lh mm
+                umma_ts(d, a0 + 0, w0 + 0 * 128, w_hi, kIdescProj, m != 0);
+                umma_ts(d, a0 + 0, w0 + 1 * 128, w_hi, kIdescProj, 1);
+                umma_ts(d, a0 + 8, w0 + 0 * 128, w_hi, kIdescProj, 1);
+                umma_ts(d, a0 + 0, w0 + 2 * 128, w_hi, kIdescProj, 1);
+                umma_ts(d, a0 + 16, w0 + 0 * 128, w_hi, kIdescProj, 1);
+                umma_ts(d, a0 + 8, w0 + 1 * 128, w_hi, kIdescProj, 1);
+                umma_commit(BAR(o + FuBars::kPEmpty + u));
+                umma_commit(BAR(FuBars::kWEmpty + u));
             }
+            __syncwarp();
         };
         int m_done = 0, n = 0, i = 0;
         for (int j = 0; j < J; ++j) {
             const int s = i & 1, slot = j & 3;
             if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done); ++m_done; }
+            if (n == 0) mbar_wait_parked(BAR(o + FuBars::kFull + s), (i >> 1) & 1);
+            mbar_wait_parked(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tcol + slot * 32;
+                const uint32_t a_s = a_lo0 + (uint32_t)(s * C) * (kTcABytes >> 4) + n;
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int o = t * FuBars::kPerTile;
-                if (n == 0) mbar_wait(BAR(o + FuBars::kFull + s), (i >> 1) & 1);
-                mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d = tmem_base + t * 256 + slot * 32;
-                    const uint32_t a_ts = a_lo0 + (uint32_t)((t * 2 + s) * C) * (kTcABytes >> 4) + n;
+                for (int c = 0; c < C; ++c)
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-#pragma unroll
-                        for (int sp = 0; sp < SPLITS; ++sp)
-                            umma_ss(d, a_ts + c * (kTcABytes >> 4), a_hi, b_lo0 + (c * SPLITS + sp) * (kTcBBytes >> 4), b_hi, kIdesc,
-                                    (c | sp) != 0);
-                    umma_commit(BAR(o + FuBars::kTFull + slot));
-                }
-                __syncwarp();
+                    for (int sp = 0; sp < SPLITS; ++sp)
+                        umma_ss(d, a_s + c * (kTcABytes >> 4), a_hi, b_lo0 + (c * SPLITS + sp) * (kTcBBytes >> 4), b_hi, kIdesc,
+                                (c | sp) != 0);
+                umma_commit(BAR(o + FuBars::kTFull + slot));
             }
+            __syncwarp();
             if (++n == kTcBlocks) { n = 0; ++i; }
         }
         for (; m_done < nchunks; ++m_done) issue_proj(m_done);
-        if (elect_one()) {
-            for (int t = 0; t < 2; ++t) umma_commit(BAR(t * FuBars::kPerTile + FuBars::kGFull));
-        }
+        if (elect_one()) umma_commit(BAR(o + FuBars::kGFull));
         __syncwarp();
+    } else if (warp == 3) {
+        // TMEM allocator only
     } else {
         // ===================== epilogue: thread == window =====================
         // Software-pipelined by one step: iteration jj runs stage A of block jj (TMEM -> pool1 ->
         // tanh) and stage B of step jj-1 (conv2 -> pool2 -> tanh -> bf16 pieces -> TMEM).  The two
         // stages touch disjoint registers, so their MUFU / FMA chains interleave in one basic block;
         // all barrier traffic sits at the top and bottom of the iteration.
-        const int t = (warp - 2) >> 2;
+        const int t = (warp - 4) >> 2;
         const int o_bar = t * FuBars::kPerTile;
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -210,21 +208,23 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
         const uint32_t swz = (uint32_t)(row & 7);
         const bool row_ok = b < p.B;
-        float pm6[kCMid], pm7[kCMid], ah[4][kCMid], ap[4][kCMid], c2c = 0.f, nan_probe = 0.f;
+        // a1 history: abuf[jj & 1] holds the 4 activations x 4 channels produced by stage A of block jj
+        float pm6[kCMid], pm7[kCMid], abuf[2][4][kCMid], c2c = 0.f, nan_probe = 0.f;
 #pragma unroll
         for (int o = 0; o < kCMid; ++o) {
             pm6[o] = 0.f; pm7[o] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { ah[i][o] = 0.f; ap[i][o] = 0.f; }
+            for (int i = 0; i < 4; ++i) { abuf[0][i][o] = 0.f; abuf[1][i][o] = 0.f; }
         }
         uint32_t Dn[32];
-        mbar_wait(BAR(o_bar + FuBars::kTFull + 0), 0);
+        mbar_wait_parked(BAR(o_bar + FuBars::kTFull + 0), 0);
         tc_fence_after();
         tmem_ld32_issue(tlane + 0, Dn);
         int n = 0, ti = 0;                                  // block-in-tile and tile index of block jj
 
-        auto iteration = [&](int jj, auto doA_, auto doB_) {
+        auto iteration = [&](int jj, auto doA_, auto doB_, auto par_) {
             constexpr bool doA = decltype(doA_)::value, doB = decltype(doB_)::value;
+            constexpr int PAR = decltype(par_)::value;      // == jj & 1 (compile-time register naming)
             const int s = ti & 1;
             const int jb = jj - 1, m = jb >> 3, kk = jb & 7, u = m & 1;
             float D[32];
@@ -238,15 +238,15 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + (jj & 3)));
                 if (jj + 1 < J) {                           // prefetch the next block's accumulators
                     const int s1 = (jj + 1) & 3;
-                    mbar_wait(BAR(o_bar + FuBars::kTFull + s1), ((jj + 1) >> 2) & 1);
+                    mbar_wait_parked(BAR(o_bar + FuBars::kTFull + s1), ((jj + 1) >> 2) & 1);
                     tc_fence_after();
                     tmem_ld32_issue(tlane + s1 * 32, Dn);
                 }
-                if (n == 0) mbar_wait(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1);   // TMA bytes visible for the tap-9 reads
+                if (n == 0) mbar_wait_parked(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1);   // TMA bytes visible for the tap-9 reads
             }
             if constexpr (doB) {
                 if (kk == 0) {                              // first store of chunk m into A buffer u
-                    mbar_wait(BAR(o_bar + FuBars::kPEmpty + u), ((m >> 1) & 1) ^ 1);
+                    mbar_wait_parked(BAR(o_bar + FuBars::kPEmpty + u), ((m >> 1) & 1) ^ 1);
                     tc_fence_after();
                 }
             }
@@ -275,7 +275,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 float c2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < kCMid; ++c) {
-                    const float A8[8] = {ah[0][c], ah[1][c], ah[2][c], ah[3][c], ap[0][c], ap[1][c], ap[2][c], ap[3][c]};
+                    // a1(step jb-1) = abuf[PAR], a1(step jb) = abuf[PAR ^ 1]
+                    const float A8[8] = {abuf[PAR][0][c], abuf[PAR][1][c], abuf[PAR][2][c], abuf[PAR][3][c],
+                                         abuf[PAR ^ 1][0][c], abuf[PAR ^ 1][1][c], abuf[PAR ^ 1][2][c], abuf[PAR ^ 1][3][c]};
 #pragma unroll
                     for (int k = 0; k < 5; ++k)
 #pragma unroll
@@ -292,20 +294,16 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 const uint32_t md = pack_bf16x2(r0, r1);
                 const float s0 = r0 - __uint_as_float(md << 16), s1v = r1 - __uint_as_float(md & 0xffff0000u);
                 const uint32_t lo = pack_bf16x2(s0, s1v);
-                const uint32_t abuf = tlane + 128 + u * 24 + kk;
-                tmem_st1(abuf, h);
-                tmem_st1(abuf + 8, md);
-                tmem_st1(abuf + 16, lo);
-#pragma unroll
-                for (int c = 0; c < kCMid; ++c)
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) ah[r][c] = ap[r][c];
+                const uint32_t acol = tlane + 128 + u * 24 + kk;
+                tmem_st1(acol, h);
+                tmem_st1(acol + 8, md);
+                tmem_st1(acol + 16, lo);
             }
-            if constexpr (doA) {
+            if constexpr (doA) {                            // a1(block jj) replaces a1(block jj-2)
 #pragma unroll
                 for (int c = 0; c < kCMid; ++c)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) ap[r][c] = an[r][c];
+                    for (int r = 0; r < 4; ++r) abuf[PAR][r][c] = an[r][c];
             }
             // ---------------- bottom: arrivals ----------------
             if constexpr (doA) {
@@ -330,13 +328,20 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         };
         using T_ = std::integral_constant<bool, true>;
         using F_ = std::integral_constant<bool, false>;
-        iteration(0, T_{}, F_{});
+        using P0 = std::integral_constant<int, 0>;
+        using P1 = std::integral_constant<int, 1>;
+        iteration(0, T_{}, F_{}, P0{});
+        int jj = 1;
 #pragma unroll 1
-        for (int jj = 1; jj < J; ++jj) iteration(jj, T_{}, T_{});
-        iteration(J, F_{}, T_{});
+        for (; jj + 1 < J; jj += 2) {                       // two steps per trip: register names alternate
+            iteration(jj, T_{}, T_{}, P1{});
+            iteration(jj + 1, T_{}, T_{}, P0{});
+        }
+        if (jj < J) { iteration(jj, T_{}, T_{}, P1{}); ++jj; }
+        if (J & 1) iteration(J, F_{}, T_{}, P1{}); else iteration(J, F_{}, T_{}, P0{});
 
         // ---- gate pre-activations of this CTA's position range -> partial[range][window][64]
-        mbar_wait(BAR(o_bar + FuBars::kGFull), 0);
+        mbar_wait_parked(BAR(o_bar + FuBars::kGFull), 0);
         tc_fence_after();
         float *dst = p.partial + ((int64_t)blockIdx.y * p.B + b) * kGates;
 #pragma unroll
@@ -355,7 +360,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 3) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
 }

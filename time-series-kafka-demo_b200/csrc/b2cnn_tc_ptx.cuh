@@ -25,6 +25,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
+// same wait with a suspend-time hint: the waiting warp is parked by the hardware (woken by the
+// completing arrive) instead of burning issue slots that the epilogue warps on its scheduler need
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
