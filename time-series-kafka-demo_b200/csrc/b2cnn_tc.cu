@@ -486,10 +486,11 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     p.wpack = reinterpret_cast<const uint8_t *>(s.d_wpack);
     p.B = (int)B; p.W = d.W; p.L = d.L;
     p.tiles_per_cta = s.tiles_per_cta; p.feats_per_cta = s.feats_per_cta; p.chunks_per_cta = s.chunks_per_cta;
-    for (int o = 0; o < kCMid; ++o) {
-        for (int c = 0; c < d.C; ++c) p.w9[o][c] = cw.w1[(c * d.K1 + 9) * kCMid + o];
-        p.b1s[o] = cw.b1[o] * k2Log2e;
-        for (int k = 0; k < 5; ++k) p.w2[o][k] = cw.w2[o * d.K2 + k];
+    for (int q2 = 0; q2 < 2; ++q2) {
+        for (int c = 0; c < d.C; ++c)
+            p.w9p[c][q2] = make_float2(cw.w1[(c * d.K1 + 9) * kCMid + 2 * q2], cw.w1[(c * d.K1 + 9) * kCMid + 2 * q2 + 1]);
+        p.b1sp[q2] = make_float2(cw.b1[2 * q2] * k2Log2e, cw.b1[2 * q2 + 1] * k2Log2e);
+        for (int k = 0; k < 5; ++k) p.w2p[q2][k] = make_float2(cw.w2[(2 * q2) * d.K2 + k], cw.w2[(2 * q2 + 1) * d.K2 + k]);
     }
     p.b2s = cw.b2 * k2Log2e;
     dim3 grid((unsigned)((B + 2 * kTcM - 1) / (2 * kTcM)), s.n_ranges);

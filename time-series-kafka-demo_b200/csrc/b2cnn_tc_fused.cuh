@@ -40,10 +40,11 @@ struct TcFusedParams {
     const uint8_t *wpack;     // [n_ranges][chunks_per_cta][kFuWChunkBytes]
     int B, W, L;
     int tiles_per_cta, feats_per_cta, chunks_per_cta;
-    float w9[kCMid][kTcMaxC];
-    float b1s[kCMid];
-    float w2[kCMid][5];
-    float b2s;
+    // epilogue constants, paired over (out-)channels (2q, 2q+1) for the packed f32x2 arithmetic
+    float2 w9p[kTcMaxC][2];    // tap k=9 of conv1: (w1[2q][c][9], w1[2q+1][c][9])
+    float2 b1sp[2];            // conv1 bias * 2 log2 e
+    float2 w2p[2][5];          // conv2 weights (w2[2q][k], w2[2q+1][k])
+    float b2s;                 // conv2 bias * 2 log2 e
 };
 
 // barrier indices (uint64_t slots)
@@ -209,12 +210,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint32_t swz = (uint32_t)(row & 7);
         const bool row_ok = b < p.B;
         // a1 history: abuf[jj & 1] holds the 4 activations x 4 channels produced by stage A of block jj
-        float pm6[kCMid], pm7[kCMid], abuf[2][4][kCMid], c2c = 0.f, nan_probe = 0.f;
+        // all per-channel state is held as float2 over channel pairs (0,1) and (2,3)
+        float2 pm6[2], pm7[2], abuf[2][4][2], nan_probe = make_float2(0.f, 0.f);
+        float c2c = 0.f;
 #pragma unroll
-        for (int o = 0; o < kCMid; ++o) {
-            pm6[o] = 0.f; pm7[o] = 0.f;
+        for (int q2 = 0; q2 < 2; ++q2) {
+            pm6[q2] = make_float2(0.f, 0.f); pm7[q2] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { abuf[0][i][o] = 0.f; abuf[1][i][o] = 0.f; }
+            for (int i = 0; i < 4; ++i) { abuf[0][i][q2] = make_float2(0.f, 0.f); abuf[1][i][q2] = make_float2(0.f, 0.f); }
         }
         uint32_t Dn[32];
         mbar_wait_parked(BAR(o_bar + FuBars::kTFull + 0), 0);
@@ -251,7 +254,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
             }
             // ---------------- middle: straight-line math ----------------
-            float an[4][kCMid];
+            float2 an[4][2];
             if constexpr (doA) {
                 const uint8_t *tile = sA_of(t, s, 0) + row * 128;
 #pragma unroll
@@ -259,41 +262,54 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
                     const float xv = __uint_as_float((uint32_t)raw << 16);
 #pragma unroll
-                    for (int o = 0; o < kCMid; ++o) pm7[o] = fmaf(p.w9[o][c], xv, pm7[o]);
+                    for (int q2 = 0; q2 < 2; ++q2) pm7[q2] = fma2(p.w9p[c][q2], make_float2(xv, xv), pm7[q2]);
                 }
 #pragma unroll
-                for (int o = 0; o < kCMid; ++o) {
-                    an[0][o] = tanh_fold(max3_nan(pm6[o], pm7[o], D[0 * 4 + o]), p.b1s[o]);
-                    an[1][o] = tanh_fold(max3_nan(D[0 * 4 + o], D[1 * 4 + o], D[2 * 4 + o]), p.b1s[o]);
-                    an[2][o] = tanh_fold(max3_nan(D[2 * 4 + o], D[3 * 4 + o], D[4 * 4 + o]), p.b1s[o]);
-                    an[3][o] = tanh_fold(max3_nan(D[4 * 4 + o], D[5 * 4 + o], D[6 * 4 + o]), p.b1s[o]);
-                    pm6[o] = D[6 * 4 + o];
-                    pm7[o] = D[7 * 4 + o];
+                for (int q2 = 0; q2 < 2; ++q2) {
+                    const int o0 = 2 * q2, o1 = 2 * q2 + 1;
+                    an[0][q2] = tanh_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, D[0 * 4 + o0]),
+                                                       max3_nan(pm6[q2].y, pm7[q2].y, D[0 * 4 + o1])), p.b1sp[q2]);
+                    an[1][q2] = tanh_fold2(make_float2(max3_nan(D[0 * 4 + o0], D[1 * 4 + o0], D[2 * 4 + o0]),
+                                                       max3_nan(D[0 * 4 + o1], D[1 * 4 + o1], D[2 * 4 + o1])), p.b1sp[q2]);
+                    an[2][q2] = tanh_fold2(make_float2(max3_nan(D[2 * 4 + o0], D[3 * 4 + o0], D[4 * 4 + o0]),
+                                                       max3_nan(D[2 * 4 + o1], D[3 * 4 + o1], D[4 * 4 + o1])), p.b1sp[q2]);
+                    an[3][q2] = tanh_fold2(make_float2(max3_nan(D[4 * 4 + o0], D[5 * 4 + o0], D[6 * 4 + o0]),
+                                                       max3_nan(D[4 * 4 + o1], D[5 * 4 + o1], D[6 * 4 + o1])), p.b1sp[q2]);
+                    pm6[q2] = make_float2(D[6 * 4 + o0], D[6 * 4 + o1]);
+                    pm7[q2] = make_float2(D[7 * 4 + o0], D[7 * 4 + o1]);
                 }
             }
             if constexpr (doB) {
-                float c2[4] = {0.f, 0.f, 0.f, 0.f};
+                // conv2: two channel-pair partial sums per output, 40 FFMA2 instead of 80 FFMA
+                float2 acc[4][2];
 #pragma unroll
-                for (int c = 0; c < kCMid; ++c) {
+                for (int r = 0; r < 4; ++r) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
+#pragma unroll
+                for (int q2 = 0; q2 < 2; ++q2) {
                     // a1(step jb-1) = abuf[PAR], a1(step jb) = abuf[PAR ^ 1]
-                    const float A8[8] = {abuf[PAR][0][c], abuf[PAR][1][c], abuf[PAR][2][c], abuf[PAR][3][c],
-                                         abuf[PAR ^ 1][0][c], abuf[PAR ^ 1][1][c], abuf[PAR ^ 1][2][c], abuf[PAR ^ 1][3][c]};
+                    const float2 A8[8] = {abuf[PAR][0][q2], abuf[PAR][1][q2], abuf[PAR][2][q2], abuf[PAR][3][q2],
+                                          abuf[PAR ^ 1][0][q2], abuf[PAR ^ 1][1][q2], abuf[PAR ^ 1][2][q2], abuf[PAR ^ 1][3][q2]};
 #pragma unroll
                     for (int k = 0; k < 5; ++k)
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) c2[r] = fmaf(p.w2[c][k], A8[r + k], c2[r]);
+                        for (int r = 0; r < 4; ++r) acc[r][q2] = fma2(p.w2p[q2][k], A8[r + k], acc[r][q2]);
                 }
-                const float f0 = tanh_fold(max3_nan(c2c, c2[0], c2[1]), p.b2s);   // feature 2*jb-3
-                const float f1 = tanh_fold(max3_nan(c2[1], c2[2], c2[3]), p.b2s);  // feature 2*jb-2
+                float c2[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float2 sacc = add2(acc[r][0], acc[r][1]);
+                    c2[r] = sacc.x + sacc.y;
+                }
+                const float2 f = tanh_fold2(make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3])),
+                                            make_float2(p.b2s, p.b2s));      // features 2*jb-3, 2*jb-2
                 c2c = c2[3];
-                nan_probe = fmaf(f0, 0.f, nan_probe);
-                nan_probe = fmaf(f1, 0.f, nan_probe);
+                nan_probe = fma2(f, make_float2(0.f, 0.f), nan_probe);
                 // three bf16 pieces of (f0, f1) -> column kk of this lane's row of the A operand
-                const uint32_t h = pack_bf16x2(f0, f1);
-                const float r0 = f0 - __uint_as_float(h << 16), r1 = f1 - __uint_as_float(h & 0xffff0000u);
-                const uint32_t md = pack_bf16x2(r0, r1);
-                const float s0 = r0 - __uint_as_float(md << 16), s1v = r1 - __uint_as_float(md & 0xffff0000u);
-                const uint32_t lo = pack_bf16x2(s0, s1v);
+                const uint32_t h = pack_bf16x2(f.x, f.y);
+                const float2 r1 = sub2(f, make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u)));
+                const uint32_t md = pack_bf16x2(r1.x, r1.y);
+                const float2 r2 = sub2(r1, make_float2(__uint_as_float(md << 16), __uint_as_float(md & 0xffff0000u)));
+                const uint32_t lo = pack_bf16x2(r2.x, r2.y);
                 const uint32_t acol = tlane + 128 + u * 24 + kk;
                 tmem_st1(acol, h);
                 tmem_st1(acol + 8, md);
@@ -301,9 +317,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             }
             if constexpr (doA) {                            // a1(block jj) replaces a1(block jj-2)
 #pragma unroll
-                for (int c = 0; c < kCMid; ++c)
+                for (int q2 = 0; q2 < 2; ++q2)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) abuf[PAR][r][c] = an[r][c];
+                    for (int r = 0; r < 4; ++r) abuf[PAR][r][q2] = an[r][q2];
             }
             // ---------------- bottom: arrivals ----------------
             if constexpr (doA) {
@@ -355,7 +371,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     *reinterpret_cast<uint4 *>(dst + half * 32 + k) = make_uint4(G[k], G[k + 1], G[k + 2], G[k + 3]);
             }
         }
-        if (row_ok && nan_probe != nan_probe) p.nanflag[b] = 1;
+        if (row_ok && (nan_probe.x != nan_probe.x || nan_probe.y != nan_probe.y)) p.nanflag[b] = 1;
     }
 
     tc_fence_before();

@@ -158,6 +158,43 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32
         " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n}"
         ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two FMAs per issue slot ------------
+__device__ __forceinline__ uint64_t pk2(float2 v) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+    return r;
+}
+__device__ __forceinline__ float2 up2(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+    return up2(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(d);
+}
+// tanh(m + bias) for two values, bias pre-multiplied by 2 log2 e (see tanh_fold)
+__device__ __forceinline__ float2 tanh_fold2(float2 m, float2 bias_scaled) {
+    const float2 a = fma2(m, make_float2(k2Log2e, k2Log2e), bias_scaled);
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a.y));
+    const float2 d = add2(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+    return fma2(make_float2(r0, r1), make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
+}
 constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
