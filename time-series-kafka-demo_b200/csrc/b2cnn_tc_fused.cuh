@@ -17,9 +17,9 @@
 //
 // CTA = 2 window tiles (2 x 128 windows) x 1 position range, one CTA per SM, 384 threads, one
 // control warp + two epilogue warps on every SM sub-partition (warp % 4):
-//   warp 0      producer: TMA boxes for both window tiles + W_ih chunks
+//   warp 0      producer: TMA boxes for both window tiles
 //   warp 1 / 2  MMA issuer of window tile 0 / 1 (conv1 bands + projection), one elected lane
-//   warp 3      TMEM allocator (512 columns)
+//   warp 3      TMEM allocator (512 columns) + producer of the W_ih chunks
 //   warps 4-7   epilogue of window tile 0 (TMEM lane quadrant = warp % 4)
 //   warps 8-11  epilogue of window tile 1
 // TMEM columns per window tile (256): conv1 ring 4 x 32 | A pieces 2 x 24 | gates 64.
@@ -106,8 +106,6 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     if (warp == 0) {
         // ===================== producer =====================
         if (lane == 0) {
-            const uint8_t *wsrc = p.wpack + (size_t)blockIdx.y * p.chunks_per_cta * kFuWChunkBytes;
-            int m_next = 0;
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i & 1, ph = (i >> 1) & 1;
                 for (int t = 0; t < 2; ++t) {
@@ -118,21 +116,6 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     for (int c = 0; c < C; ++c)
                         tma_load_3d(smem_u32(sA_of(t, s, c)), &tmap, T0 + kTcAdv * i, c, b_cta + t * kTcM, BAR(o + FuBars::kFull + s));
                 }
-                while (m_next < nchunks && 8 * m_next <= 7 * i + 15 - kFuLag) {   // never wait on a chunk whose consumer needs a tile not issued yet
-                    const int u = m_next & 1;
-                    mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
-                    mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
-                    bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m_next * kFuWChunkBytes, kFuWChunkBytes,
-                                 BAR(FuBars::kWFull + u));
-                    ++m_next;
-                }
-            }
-            for (; m_next < nchunks; ++m_next) {
-                const int u = m_next & 1;
-                mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((m_next >> 1) & 1) ^ 1);
-                mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
-                bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m_next * kFuWChunkBytes, kFuWChunkBytes,
-                             BAR(FuBars::kWFull + u));
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -194,7 +177,19 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         if (elect_one()) umma_commit(BAR(o + FuBars::kGFull));
         __syncwarp();
     } else if (warp == 3) {
-        // TMEM allocator only
+        // ===================== W_ih chunk producer (and TMEM allocator) =====================
+        // Separate from the window-tile producer: a chunk may only be refilled after BOTH window
+        // tiles projected the chunk two back, and that wait must never delay the next A-tile request.
+        if (lane == 0) {
+            const uint8_t *wsrc = p.wpack + (size_t)blockIdx.y * p.chunks_per_cta * kFuWChunkBytes;
+            for (int m = 0; m < nchunks; ++m) {
+                const int u = m & 1;
+                mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((m >> 1) & 1) ^ 1);
+                mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
+                bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m * kFuWChunkBytes, kFuWChunkBytes,
+                             BAR(FuBars::kWFull + u));
+            }
+        }
     } else {
         // ===================== epilogue: thread == window =====================
         // Software-pipelined by one step: iteration jj runs stage A of block jj (TMEM -> pool1 ->
