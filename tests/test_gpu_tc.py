@@ -16,10 +16,11 @@ DEV = "cuda:0"
 TOL = 1e-4
 
 
-def _pair(C, W, path="tensorcore", tc_splits=3, seed=0):
-    oarch = O.stretched(O.ARCH_MYCNN5, C, W)
+def _pair(C, W, path="tensorcore", tc_splits=3, seed=0, kind="mycnn5"):
+    oarch = O.stretched(O.ARCHS[kind], C, W)
     ref = O.make_ref(oarch, seed=seed)
-    m = tskd_b200.B200MyCNN(tskd_b200.ARCH_PRESETS["mycnn5"].with_shape(C, W), path=path, tc_splits=tc_splits).to(DEV)
+    arch = replace(tskd_b200.ARCH_PRESETS[kind].with_shape(C, W), age_coef=oarch.age_coef)
+    m = tskd_b200.B200MyCNN(arch, has_out12=oarch.has_out12, path=path, tc_splits=tc_splits).to(DEV)
     m.load_state_dict(ref.state_dict())
     return ref, m
 
@@ -93,10 +94,36 @@ def test_tc_nan_inf_windows_are_recomputed_exactly():
     assert np.nanmax(np.abs(fg - fw)) < 2e-5
 
 
+@pytest.mark.parametrize("kind,C,W,B,dist", [
+    ("mycnn5", 3, 7500, 150, "normal"),     # W % 8 == 4: rows staged into a 16-byte-pitch scratch for TMA
+    ("mycnn5", 3, 37500, 20, "physio"),
+    ("mycnn5", 2, 1533, 40, "normal"),      # odd W
+    ("mycnn3", 3, 7504, 200, "normal"),     # MyCNN2/3/4 geometry (k1=5, pool(2,2)) on the fused kernel
+    ("mycnn3", 3, 7500, 130, "physio"),
+    ("mycnn3", 1, 2048, 64, "normal"),
+    ("mycnn3", 3, 75000, 6, "normal"),
+])
+def test_tc_other_geometries_and_unaligned_windows(kind, C, W, B, dist):
+    ref, m = _pair(C, W, kind=kind)
+    x = tskd_b200.synth.make_windows(B, C, W, dist, seed=41, dtype=torch.bfloat16)
+    ages = tskd_b200.synth.make_ages(B, seed=41)
+    want = O.ref_independent(ref, x.float(), ages).numpy()
+    got = m.predict(x.to(DEV), ages.to(DEV)).cpu().numpy()
+    assert m.last_path == "tensorcore" and rel_err(got, want) <= TOL, rel_err(got, want)
+    if kind == "mycnn5":
+        fw = O.ref_features(ref, x.float()).numpy()
+        fg = m.features(x.to(DEV)).cpu().numpy()
+        assert m.last_path == "tensorcore" and np.abs(fg - fw).max() < 2e-5
+    seq = m(x[:24].to(DEV), ages[:24].to(DEV)).cpu().numpy()
+    assert rel_err(seq, O.ref_sequence(ref, x[:24].float(), ages[:24]).numpy()) <= TOL
+
+
 def test_tc_refuses_unsupported_shapes_instead_of_falling_back():
-    _, m = _pair(3, 7500)            # 7500 % 8 != 0: rows are not 16-byte aligned for TMA
+    ref = O.make_ref(O.stretched(O.ARCH_MYCNN5, 5, 2048), seed=0)       # 5 channels: no tensor-core instantiation
+    m = tskd_b200.B200MyCNN(tskd_b200.ARCH_PRESETS["mycnn5"].with_shape(5, 2048), path="tensorcore").to(DEV)
+    m.load_state_dict(ref.state_dict())
     with pytest.raises(RuntimeError, match="tensor"):
-        m.predict(torch.zeros(4, 3, 7500, dtype=torch.bfloat16, device=DEV))
+        m.predict(torch.zeros(4, 5, 2048, dtype=torch.bfloat16, device=DEV))
     _, m = _pair(3, 7504)
     with pytest.raises(RuntimeError, match="tensor"):
         m.predict(torch.zeros(4, 3, 7504, dtype=torch.float32, device=DEV))   # fp32 input

@@ -298,9 +298,14 @@ static float bf16_to_f(uint16_t h) {
     return f;
 }
 
+// MyCNN2/3/4 geometry: fused kernel only (ARCH 1)
+static bool arch1_ok(const Dims &d) {
+    return d.K1 == 5 && d.K2 == 5 && d.PK == 2 && d.PS == 2 && d.C >= 1 && d.C <= 3 && d.act == B2CNN_ACT_TANH &&
+           !d.has_affine && d.L >= 32;
+}
 static bool arch_ok(const Dims &d) {
     return d.K1 == 10 && d.K2 == 5 && d.PK == 3 && d.PS == 2 && d.C >= 1 && d.C <= kTcMaxC &&
-           d.act == B2CNN_ACT_TANH && !d.has_affine && (d.W % 8) == 0 && d.L >= 32;
+           d.act == B2CNN_ACT_TANH && !d.has_affine && d.L >= 32;
 }
 
 static int tiles_per_cta_for(const Dims &d);
@@ -309,7 +314,8 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
                cudaStream_t st) {
     s.ready = false;
     s.splits = splits;
-    if (!arch_ok(d)) return 0;                 // not an error: this shape takes the generic path
+    s.fused_ready = false;
+    if (!arch_ok(d) && !arch1_ok(d)) return 0;   // not an error: this shape takes the generic path
     if (!get_encode()) return 0;
     // band matrices: piece sp of T_c[k][(s,o)] = w1[o][c][k-s], stored as UMMA K-major
     // no-swizzle core matrices: byte = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2, n = s*4+o
@@ -333,6 +339,7 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
     if (cudaMemcpyAsync(s.d_bmats, host.data(), host.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) { g_tc_err = "upload band matrices"; return -1; }
     s.ready = true;
+    s.has_v1 = arch_ok(d);
     // ---- fused kernel: W_ih_l0 packed per (range, chunk)
     s.fused_ready = false;
     s.tiles_per_cta = tiles_per_cta_for(d);
@@ -345,7 +352,7 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
         if (cudaMalloc(&s.d_wpack, bytes) != cudaSuccess) { g_tc_err = "cudaMalloc(packed W_ih)"; return -1; }
         const int64_t total = (int64_t)s.n_ranges * s.chunks_per_cta * 1024;
         tc_pack_wih_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_wih0, reinterpret_cast<uint8_t *>(s.d_wpack), d.L,
-                                                                          s.feats_per_cta, s.chunks_per_cta, s.n_ranges);
+                                                                          s.feats_per_cta, s.chunks_per_cta, s.n_ranges, d.K1 == 10 ? 3 : 2);
         if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { g_tc_err = "pack W_ih"; return -1; }
         s.fused_ready = true;
     }
@@ -362,14 +369,56 @@ void tc_release(TcState &s) {
 
 bool tc_supported(const TcState &s, const Dims &d, int dtype, int64_t B, int mode) {
     (void)mode; (void)B;
-    return s.ready && dtype == B2CNN_DTYPE_BF16 && arch_ok(d);
+    return s.ready && dtype == B2CNN_DTYPE_BF16 && (arch_ok(d) || (arch1_ok(d) && s.fused_ready && s.opt_fused));
 }
-bool tc_can_emit_features(const TcState &s) { return s.ready; }
+bool tc_can_emit_features(const TcState &s) { return s.ready && s.has_v1; }
 
-// tc workspace: nan flags [B] + list [B] + count
-int64_t tc_workspace_bytes(const TcState &s, const Dims &, int64_t B) {
+// A TMA tensor map needs a row pitch that is a multiple of 16 bytes.  Windows whose length is not a
+// multiple of 8 samples (7500, 37500 ...) are copied once into a pitch-aligned scratch (costs one
+// extra read + write of the input; W % 8 == 0, e.g. the headline 75000, streams straight from x).
+static int64_t padded_w(const Dims &d) { return (d.W + 7) & ~7; }
+static int64_t flags_bytes(int64_t B) { return ((2 * B + 64) * 4 + 255) / 256 * 256; }
+static int64_t xpad_bytes(const Dims &d, int64_t B) { return (d.W % 8) ? (B * d.C * padded_w(d) * 2 + 255) / 256 * 256 : 0; }
+
+// tc workspace: nan flags [B] + list [B] + count, then the optional pitch-aligned copy of x
+int64_t tc_workspace_bytes(const TcState &s, const Dims &d, int64_t B) {
     if (!s.ready) return 0;
-    return ((2 * B + 64) * 4 + 255) / 256 * 256;
+    return flags_bytes(B) + xpad_bytes(d, B);
+}
+
+template <int VEC>
+__global__ void tc_repack_rows_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int64_t rows, int W, int Wp) {
+    const int per_row = Wp / VEC;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        const uint16_t *in = src + r * W;
+        uint16_t *out = dst + r * Wp;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+            if (VEC == 4) {
+                uint2 v = make_uint2(0u, 0u);
+                if (i * 4 < W) v = *reinterpret_cast<const uint2 *>(in + i * 4);     // W % 4 == 0 here
+                *reinterpret_cast<uint2 *>(out + i * 4) = v;
+            } else {
+                out[i] = i < W ? in[i] : (uint16_t)0;
+            }
+        }
+    }
+}
+
+// returns the pointer / pitch the tensor map must describe (x itself when already aligned)
+static const void *tc_stage_input(const Dims &d, const void *x, int64_t B, void *scratch_after_flags, int64_t *pitch,
+                                  int *launches, cudaStream_t st) {
+    *pitch = d.W;
+    if ((d.W % 8) == 0) return x;
+    const int64_t rows = B * d.C;
+    const int Wp = (int)padded_w(d);
+    dim3 grid(8, (unsigned)(rows < 16384 ? rows : 16384));
+    if (d.W % 4 == 0)
+        tc_repack_rows_kernel<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<uint16_t *>(scratch_after_flags), rows, d.W, Wp);
+    else
+        tc_repack_rows_kernel<1><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<uint16_t *>(scratch_after_flags), rows, d.W, Wp);
+    *pitch = Wp;
+    ++*launches;
+    return scratch_after_flags;
 }
 
 static int tiles_per_cta_for(const Dims &d) {
@@ -379,12 +428,12 @@ static int tiles_per_cta_for(const Dims &d) {
     return 37;
 }
 
-static int launch_tc_kernel(const TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B,
+static int launch_tc_kernel(const TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t pitch, int64_t B,
                             float *feats, int64_t sB, int64_t sP, int *nanflag, cudaStream_t st, const char **err) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
     CUtensorMap tm;
     cuuint64_t gdim[3] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)B};
-    cuuint64_t gstr[2] = {(cuuint64_t)d.W * 2, (cuuint64_t)d.C * d.W * 2};
+    cuuint64_t gstr[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)d.C * pitch * 2};
     cuuint32_t box[3] = {64, 1, kTcM};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x), gdim, gstr, box, estr,
@@ -429,17 +478,20 @@ int tc_frontend(TcState &s, const Dims &d, const ConvWeights &cw, const void *x,
                 int64_t sB, int64_t sP, void *ws, int num_sms, cudaStream_t st, const char **err) {
     int *flags = reinterpret_cast<int *>(ws);
     const bool own = flags == nullptr;
-    if (own && cudaMallocAsync(&flags, sizeof(int) * (2 * B + 64), st) != cudaSuccess) { *err = "cudaMallocAsync"; return -1; }
+    if (own && cudaMallocAsync(&flags, (size_t)tc_workspace_bytes(s, d, B), st) != cudaSuccess) { *err = "cudaMallocAsync"; return -1; }
     int *list = flags + B, *count = list + B;
     int launches = -1;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) {
         *err = "memset flags";
     } else {
-        int n = launch_tc_kernel(s, d, cw, x, B, feats, sB, sP, flags, st, err);
+        int staged = 0;
+        int64_t pitch = d.W;
+        const void *xin = tc_stage_input(d, x, B, reinterpret_cast<char *>(flags) + flags_bytes(B), &pitch, &staged, st);
+        int n = launch_tc_kernel(s, d, cw, xin, pitch, B, feats, sB, sP, flags, st, err);
         if (n >= 0) {
             tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
             int m = launch_frontend_generic_listed(d, cw, x, B2CNN_DTYPE_BF16, B, feats, sB, sP, list, count, st, num_sms, err);
-            if (m >= 0) launches = n + 1 + m;
+            if (m >= 0) launches = staged + n + 1 + m;
         }
     }
     if (own) cudaFreeAsync(flags, st);
@@ -454,14 +506,14 @@ int tc_features(TcState &s, const Dims &d, const ConvWeights &cw, const void *x,
 
 
 bool tc_fused_supported(const TcState &s, const Dims &d, int dtype) {
-    return s.ready && s.fused_ready && s.opt_fused && dtype == B2CNN_DTYPE_BF16 && arch_ok(d) && d.C <= 3;
+    return s.ready && s.fused_ready && s.opt_fused && dtype == B2CNN_DTYPE_BF16 && (arch_ok(d) || arch1_ok(d)) && d.C <= 3;
 }
 int tc_partial_slices(const TcState &s) { return s.fused_ready ? s.n_ranges : 0; }
 
-static int make_tmap(const Dims &d, const void *x, int64_t B, CUtensorMap *tm, const char **err) {
+static int make_tmap(const Dims &d, const void *x, int64_t pitch, int64_t B, CUtensorMap *tm, const char **err) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
     cuuint64_t gdim[3] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)B};
-    cuuint64_t gstr[2] = {(cuuint64_t)d.W * 2, (cuuint64_t)d.C * d.W * 2};
+    cuuint64_t gstr[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)d.C * pitch * 2};
     cuuint32_t box[3] = {64, 1, kTcM};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(x), gdim, gstr, box, estr,
@@ -477,8 +529,11 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     int *flags = reinterpret_cast<int *>(ws);
     int *list = flags + B, *count = list + B;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+    int staged = 0;
+    int64_t pitch = d.W;
+    const void *xin = tc_stage_input(d, x, B, reinterpret_cast<char *>(flags) + flags_bytes(B), &pitch, &staged, st);
     CUtensorMap tm;
-    if (make_tmap(d, x, B, &tm, err) != 0) return -1;
+    if (make_tmap(d, xin, pitch, B, &tm, err) != 0) return -1;
     TcFusedParams p;
     memset(&p, 0, sizeof p);
     p.partial = partial; p.nanflag = flags;
@@ -488,7 +543,8 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     p.tiles_per_cta = s.tiles_per_cta; p.feats_per_cta = s.feats_per_cta; p.chunks_per_cta = s.chunks_per_cta;
     for (int q2 = 0; q2 < 2; ++q2) {
         for (int c = 0; c < d.C; ++c)
-            p.w9p[c][q2] = make_float2(cw.w1[(c * d.K1 + 9) * kCMid + 2 * q2], cw.w1[(c * d.K1 + 9) * kCMid + 2 * q2 + 1]);
+            p.w9p[c][q2] = d.K1 == 10 ? make_float2(cw.w1[(c * d.K1 + 9) * kCMid + 2 * q2], cw.w1[(c * d.K1 + 9) * kCMid + 2 * q2 + 1])
+                                      : make_float2(0.f, 0.f);
         p.b1sp[q2] = make_float2(cw.b1[2 * q2] * k2Log2e, cw.b1[2 * q2 + 1] * k2Log2e);
         for (int k = 0; k < 5; ++k) p.w2p[q2][k] = make_float2(cw.w2[(2 * q2) * d.K2 + k], cw.w2[(2 * q2 + 1) * d.K2 + k]);
     }
@@ -496,18 +552,19 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     dim3 grid((unsigned)((B + 2 * kTcM - 1) / (2 * kTcM)), s.n_ranges);
     const size_t smem = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
                         FuBars::kTotal * 8 + 16;
-#define FU_LAUNCH(CC, SS)                                                                              \
-    if (d.C == CC && s.splits == SS) {                                                                 \
-        cudaError_t e = cudaFuncSetAttribute(tc_fused_kernel<CC, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    const int arch_id = d.K1 == 10 ? 0 : 1;
+#define FU_LAUNCH(CC, SS, AA)                                                                          \
+    if (d.C == CC && s.splits == SS && arch_id == AA) {                                                \
+        cudaError_t e = cudaFuncSetAttribute(tc_fused_kernel<CC, SS, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }                             \
-        tc_fused_kernel<CC, SS><<<grid, kFuThreads, smem, st>>>(tm, p);                                \
+        tc_fused_kernel<CC, SS, AA><<<grid, kFuThreads, smem, st>>>(tm, p);                            \
     } else
-    FU_LAUNCH(3, 3) FU_LAUNCH(3, 2) FU_LAUNCH(2, 3) FU_LAUNCH(1, 3)
+    FU_LAUNCH(3, 3, 0) FU_LAUNCH(3, 2, 0) FU_LAUNCH(2, 3, 0) FU_LAUNCH(1, 3, 0) FU_LAUNCH(3, 3, 1) FU_LAUNCH(2, 3, 1) FU_LAUNCH(1, 3, 1)
     { *err = "no fused instantiation for this channel count / split"; return -1; }
 #undef FU_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
-    int launches = 1;
+    int launches = 1 + staged;
     tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
     ++launches;
     int n = launch_reduce_gates(partial, s.n_ranges, B, hw, gates, st, err);

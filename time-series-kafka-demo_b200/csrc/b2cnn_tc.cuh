@@ -10,6 +10,7 @@ struct TcState {
     void *d_bmats = nullptr;     // Toeplitz-expanded conv1 weights, bf16 pieces (see b2cnn_tc.cu)
     void *d_wpack = nullptr;     // W_ih_l0 packed per (position range, 16-position chunk), 3 bf16 pieces
     int tiles_per_cta = 37, feats_per_cta = 514, chunks_per_cta = 33, n_ranges = 1;
+    bool has_v1 = false;         // tc_frontend_kernel (features out) exists for this geometry (MyCNN5 only)
     bool fused_ready = false;    // fused conv + projection kernel usable (C <= 3)
     int64_t opt_fused = 1;
 };

@@ -54,7 +54,11 @@ struct FuBars {
     static constexpr int kWFull = 2 * kPerTile, kWEmpty = kWFull + 2, kTotal = kWEmpty + 2;
 };
 
-template <int C, int SPLITS>
+// ARCH 0: MyCNN5 geometry (K1=10, pool(3,2)) -- bin/models.py.
+// ARCH 1: MyCNN2/3/4 geometry (K1=5, pool(2,2)) -- bin/explore_torch copy.ipynb:189-277: every tap
+//         fits the 16-sample slice (no tap-9 patch), pooling pairs stay inside a block (no carry),
+//         and a step emits features 2j-2, 2j-1 instead of 2j-3, 2j-2.
+template <int C, int SPLITS, int ARCH>
 __global__ void __launch_bounds__(kFuThreads, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcFusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -72,7 +76,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const int b_cta = blockIdx.x * 2 * kTcM;
     const int p0 = blockIdx.y * p.feats_per_cta;
     const int nfeat = min(p.feats_per_cta, p.L - p0);
-    const int nsteps_needed = (nfeat + 4) / 2;
+    constexpr int FOFF = ARCH == 0 ? 3 : 2;           // step j emits features 2j-FOFF, 2j-FOFF+1
+    const int nsteps_needed = (nfeat + FOFF - 1) / 2 + 1;
     const int ntiles = (nsteps_needed + kTcBlocks - 1) / kTcBlocks;
     const int J = ntiles * kTcBlocks;                 // steps actually run
     const int nchunks = (J + 7) / 8;
@@ -251,27 +256,39 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // ---------------- middle: straight-line math ----------------
             float2 an[4][2];
             if constexpr (doA) {
-                const uint8_t *tile = sA_of(t, s, 0) + row * 128;
+                if constexpr (ARCH == 0) {
+                    const uint8_t *tile = sA_of(t, s, 0) + row * 128;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
-                    const float xv = __uint_as_float((uint32_t)raw << 16);
+                    for (int c = 0; c < C; ++c) {
+                        const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
+                        const float xv = __uint_as_float((uint32_t)raw << 16);
 #pragma unroll
-                    for (int q2 = 0; q2 < 2; ++q2) pm7[q2] = fma2(p.w9p[c][q2], make_float2(xv, xv), pm7[q2]);
-                }
+                        for (int q2 = 0; q2 < 2; ++q2) pm7[q2] = fma2(p.w9p[c][q2], make_float2(xv, xv), pm7[q2]);
+                    }
 #pragma unroll
-                for (int q2 = 0; q2 < 2; ++q2) {
-                    const int o0 = 2 * q2, o1 = 2 * q2 + 1;
-                    an[0][q2] = tanh_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, D[0 * 4 + o0]),
-                                                       max3_nan(pm6[q2].y, pm7[q2].y, D[0 * 4 + o1])), p.b1sp[q2]);
-                    an[1][q2] = tanh_fold2(make_float2(max3_nan(D[0 * 4 + o0], D[1 * 4 + o0], D[2 * 4 + o0]),
-                                                       max3_nan(D[0 * 4 + o1], D[1 * 4 + o1], D[2 * 4 + o1])), p.b1sp[q2]);
-                    an[2][q2] = tanh_fold2(make_float2(max3_nan(D[2 * 4 + o0], D[3 * 4 + o0], D[4 * 4 + o0]),
-                                                       max3_nan(D[2 * 4 + o1], D[3 * 4 + o1], D[4 * 4 + o1])), p.b1sp[q2]);
-                    an[3][q2] = tanh_fold2(make_float2(max3_nan(D[4 * 4 + o0], D[5 * 4 + o0], D[6 * 4 + o0]),
-                                                       max3_nan(D[4 * 4 + o1], D[5 * 4 + o1], D[6 * 4 + o1])), p.b1sp[q2]);
-                    pm6[q2] = make_float2(D[6 * 4 + o0], D[6 * 4 + o1]);
-                    pm7[q2] = make_float2(D[7 * 4 + o0], D[7 * 4 + o1]);
+                    for (int q2 = 0; q2 < 2; ++q2) {
+                        const int o0 = 2 * q2, o1 = 2 * q2 + 1;
+                        an[0][q2] = tanh_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, D[0 * 4 + o0]),
+                                                           max3_nan(pm6[q2].y, pm7[q2].y, D[0 * 4 + o1])), p.b1sp[q2]);
+                        an[1][q2] = tanh_fold2(make_float2(max3_nan(D[0 * 4 + o0], D[1 * 4 + o0], D[2 * 4 + o0]),
+                                                           max3_nan(D[0 * 4 + o1], D[1 * 4 + o1], D[2 * 4 + o1])), p.b1sp[q2]);
+                        an[2][q2] = tanh_fold2(make_float2(max3_nan(D[2 * 4 + o0], D[3 * 4 + o0], D[4 * 4 + o0]),
+                                                           max3_nan(D[2 * 4 + o1], D[3 * 4 + o1], D[4 * 4 + o1])), p.b1sp[q2]);
+                        an[3][q2] = tanh_fold2(make_float2(max3_nan(D[4 * 4 + o0], D[5 * 4 + o0], D[6 * 4 + o0]),
+                                                           max3_nan(D[4 * 4 + o1], D[5 * 4 + o1], D[6 * 4 + o1])), p.b1sp[q2]);
+                        pm6[q2] = make_float2(D[6 * 4 + o0], D[6 * 4 + o1]);
+                        pm7[q2] = make_float2(D[7 * 4 + o0], D[7 * 4 + o1]);
+                    }
+                } else {
+                    // pool(2,2): pooled position 4j+i = max(pre[8j+2i], pre[8j+2i+1])
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) {
+                        const int o0 = 2 * q2, o1 = 2 * q2 + 1;
+#pragma unroll
+                        for (int i2 = 0; i2 < 4; ++i2)
+                            an[i2][q2] = tanh_fold2(make_float2(max_nan(D[(2 * i2) * 4 + o0], D[(2 * i2 + 1) * 4 + o0]),
+                                                                max_nan(D[(2 * i2) * 4 + o1], D[(2 * i2 + 1) * 4 + o1])), p.b1sp[q2]);
+                    }
                 }
             }
             if constexpr (doB) {
@@ -295,9 +312,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     const float2 sacc = add2(acc[r][0], acc[r][1]);
                     c2[r] = sacc.x + sacc.y;
                 }
-                const float2 f = tanh_fold2(make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3])),
-                                            make_float2(p.b2s, p.b2s));      // features 2*jb-3, 2*jb-2
-                c2c = c2[3];
+                float2 f;                                                    // features 2*jb-FOFF, 2*jb-FOFF+1
+                if constexpr (ARCH == 0) {
+                    f = tanh_fold2(make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3])), make_float2(p.b2s, p.b2s));
+                    c2c = c2[3];
+                } else {
+                    f = tanh_fold2(make_float2(max_nan(c2[0], c2[1]), max_nan(c2[2], c2[3])), make_float2(p.b2s, p.b2s));
+                }
                 nan_probe = fma2(f, make_float2(0.f, 0.f), nan_probe);
                 // three bf16 pieces of (f0, f1) -> column kk of this lane's row of the A operand
                 const uint32_t h = pack_bf16x2(f.x, f.y);
@@ -382,14 +403,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // step j); positions outside the range or beyond L get zero weights, which also masks the
 // stream's warm-up / tail garbage.
 __global__ void tc_pack_wih_kernel(const float *__restrict__ wih, uint8_t *__restrict__ out, int L, int feats_per_cta,
-                                   int chunks_per_cta, int n_ranges) {
+                                   int chunks_per_cta, int n_ranges, int foff) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)n_ranges * chunks_per_cta * 1024;
     if (e >= total) return;
     const int k = (int)(e & 15), g = (int)((e >> 4) & 63);
     const int64_t cm = e >> 10;
     const int m = (int)(cm % chunks_per_cta), pr = (int)(cm / chunks_per_cta);
-    const int prel = 16 * m - 3 + k;
+    const int prel = 16 * m - foff + k;              // step j emits features 2j-foff, 2j-foff+1
     const int pos = pr * feats_per_cta + prel;
     float w = 0.f;
     if (prel >= 0 && prel < feats_per_cta && pos < L) w = wih[(int64_t)g * L + pos];
