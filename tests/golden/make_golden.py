@@ -157,7 +157,38 @@ def golden_stretched():
         print(kind, C, W, B, "L_out", L, rec["ind_logits"][:2])
 
 
+# ---------------------------------------------------------------- 4. streaming replay (configs[4])
+def golden_replay():
+    """The shipped numerics record p000194 (7 signals @ 1/60 Hz, 1625 samples) replayed through the
+    restated window logic (tskd_b200/stream.py builds x_arr); expected scores = the UNMODIFIED
+    reference model called once per window exactly as predictStream.py:154-162 does."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    import tskd_b200.stream as S
+    d = f"{REF}/data/waveform/physionet.org/files/mimic3wdb-matched/1.0/p00/p000194"
+    rec = S.NumericsRecord.from_wfdb_files(f"{d}/p000194-2112-05-23-14-34n.hea", f"{d}/3400942n.dat")
+    csum = [int(np.int16(rec.raw[:, i].astype(np.int64).sum() & 0xffff)) for i in range(rec.raw.shape[1])]
+    assert csum == [3240, 20492, 29088, 10310, -27206, -29717, -28780], csum      # header checksums
+    x, t0 = S.assemble_windows(rec)
+    m = load_ckpt(5)
+    probs, logits = [], []
+    with torch.no_grad():
+        for i in range(x.shape[0]):
+            x_arr = torch.from_numpy(x[i:i + 1]).type(torch.FloatTensor).float()          # predictStream.py:155
+            a_arr = torch.from_numpy(np.array(65.0)).type(torch.FloatTensor).unsqueeze(0)  # :149,156
+            output = m(x_arr, a_arr)                                                       # :157
+            y = torch.sigmoid(output)                                                      # :160
+            logits.append(output.numpy()[0]); probs.append(y.numpy().tolist()[0])
+    np.savez_compressed(os.path.join(OUT, "p000194_replay.npz"), raw=rec.raw, names=np.array(rec.names),
+                        gains=rec.gains, baselines=rec.baselines, fs=np.array(rec.fs),
+                        logits=np.array(logits, dtype=np.float32), probs=np.array(probs, dtype=np.float64),
+                        t0=t0, x_first=x[0], x_last=x[-1])
+    print("replay:", x.shape, "selected", [rec.names[i] for i in S.selected_signals(rec)], logits[:3], probs[-1])
+
+
 if __name__ == "__main__":
+    if "--replay-only" in sys.argv:
+        golden_replay(); sys.exit(0)
     golden_mycnn5()
     golden_old_ckpts()
     golden_stretched()
+    golden_replay()

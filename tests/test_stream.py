@@ -1,0 +1,76 @@
+"""Streaming replay (BASELINE.json configs[4]) at the model boundary: the restated window logic
+(tskd_b200/stream.py) on CPU, and GPU predict() parity on identical x_arr against the scores the
+unmodified reference produced for the shipped record p000194 (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import tskd_b200
+from tskd_b200 import stream as S
+from conftest import load_golden, rel_err
+from oracle import mycnn_torch as O
+
+
+def _record(g):
+    return S.NumericsRecord(tuple(str(n) for n in g["names"]), g["gains"], g["baselines"], float(g["fs"]), g["raw"])
+
+
+def test_record_decoding_and_channel_selection():
+    g, _ = load_golden("p000194_replay.npz")
+    rec = _record(g)
+    assert rec.raw.shape == (1625, 7) and abs(rec.fs - 1 / 60) < 1e-9
+    # 16-bit column checksums of the header (p000194-2112-05-23-14-34n.hea:2-8)
+    csum = [int(np.int16(rec.raw[:, i].astype(np.int64).sum() & 0xffff)) for i in range(7)]
+    assert csum == [3240, 20492, 29088, 10310, -27206, -29717, -28780]
+    # only the names config.cfg:23 lists are selected; "NBPSys" != "NBP Sys" (sendStream.py:46)
+    assert [rec.names[i] for i in S.selected_signals(rec)] == ["HR", "PULSE", "RESP", "SpO2"]
+    p = rec.physical
+    assert np.isnan(p[rec.raw == -32768]).all() and np.nanmax(p[:, 0]) < 300
+
+
+def test_grid_smoothing_semantics():
+    fs = 1 / 60.0
+    s = np.array([np.nan, 60.0, 90.0, np.nan, 30.0, 30.0, 30.0])      # one sample per minute
+    g = S.smooth_to_grid(s, fs)
+    assert len(g) == 6 * 12 + 1
+    assert g[0] == 60.0                       # nothing valid yet -> back-filled from the first valid mean
+    assert g[12] == 60.0                      # window (-120, 60]: {nan, 60}
+    assert g[24] == 75.0                      # (−60, 120]: {nan, 60, 90} -> 75
+    assert g[35] == 75.0 and g[36] == 75.0    # (0, 180]: {60, 90, nan}
+    assert g[48] == 60.0                      # (60, 240]: {90, nan, 30}
+    assert g[72] == 30.0
+    z = S.smooth_to_grid(np.full(5, np.nan), fs)
+    assert (z == 0).all()                     # never observed -> zeros (processStream.py 0-fill)
+
+
+def test_window_assembly_matches_golden_inputs():
+    g, _ = load_golden("p000194_replay.npz")
+    x, t0 = S.assemble_windows(_record(g))
+    assert x.shape == (1615, 10, 120) and x.dtype == np.float64
+    assert np.array_equal(x[0], g["x_first"]) and np.array_equal(x[-1], g["x_last"])
+    assert (x[:, 4:, :] == 0).all()           # the six signals the record lacks (predictStream.py:131)
+    assert t0[1] - t0[0] == 60.0 and np.array_equal(t0, g["t0"])
+    # consecutive windows overlap by 108 of 120 points (600 s window, 60 s slide)
+    assert np.array_equal(x[1, 0, :108], x[0, 0, 12:])
+
+
+@pytest.mark.gpu
+def test_replay_parity_gpu_vs_reference_scores():
+    g, _ = load_golden("p000194_replay.npz")
+    g5, sd = load_golden("mycnn5_xtestinput.npz")
+    rec = _record(g)
+    model = tskd_b200.B200MyCNN.from_reference(sd).to("cuda:0")
+    rows = S.replay(model, rec, subject_id=194, age=65.0)               # ONE batched predict()
+    assert len(rows) == 1615 and rows[0][0] == 194 and rows[1][1] - rows[0][1] == 60.0
+    probs = np.array([r[2] for r in rows])
+    assert rel_err(probs, g["probs"]) <= 1e-4                            # vs the unmodified reference
+    rows_mb = S.replay(model, rec, subject_id=194, age=65.0, micro_batch=16)   # BATCHSIZE = 16 (config.cfg:26)
+    assert np.array_equal(np.array([r[2] for r in rows_mb]), probs)
+    # logits on identical x_arr: GPU vs golden vs oracle per-window loop
+    x, _ = S.assemble_windows(rec)
+    xt = torch.from_numpy(x).float()
+    logit = model.predict(xt.cuda(), 65.0).cpu().numpy()
+    assert rel_err(logit, g["logits"]) <= 1e-4
+    ref = O.RefMyCNN(O.ARCH_MYCNN5); ref.load_state_dict(sd); ref.eval()
+    want = O.ref_independent_loop(ref, xt[:200], torch.full((200,), 65.0)).numpy()
+    assert np.array_equal(want, g["logits"][:200]) and rel_err(logit[:200], want) <= 1e-4

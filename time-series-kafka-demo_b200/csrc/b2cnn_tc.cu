@@ -422,10 +422,15 @@ static const void *tc_stage_input(const Dims &d, const void *x, int64_t B, void 
 }
 
 static int tiles_per_cta_for(const Dims &d) {
-    // ~514 features per CTA: 37 position ranges x 32 window tiles = 1184 CTAs = 4 waves of 296
-    (void)d;
+    // About 37 position ranges per window whatever its length (depends on L only, so a window's
+    // summation order never depends on the batch): L=18745 -> 37 tiles (514 features) per CTA and
+    // 37 ranges x 16 window-tile pairs = 592 CTAs = 4 waves of 148 at B=4096; shorter windows get
+    // proportionally shorter ranges so that small batches still fill the SMs.
     if (const char *e = getenv("B2CNN_TC_TILES")) { const int v = atoi(e); if (v >= 1 && v <= 4096) return v; }
-    return 37;
+    int nt = ((d.L + 36) / 37 + 4 + 13) / 14;
+    if (nt < 2) nt = 2;
+    if (nt > 37) nt = 37;
+    return nt;
 }
 
 static int launch_tc_kernel(const TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t pitch, int64_t B,

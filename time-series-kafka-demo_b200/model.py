@@ -133,15 +133,19 @@ class B200MyCNN(nn.Module):
         return lib, self._handle
 
     def _release(self):
-        if self._handle is not None:
+        h = self.__dict__.get("_handle")
+        if h is not None:
+            self.__dict__["_handle"] = None      # plain dict write: safe during interpreter shutdown
             try:
-                capi.load_library().b2cnn_destroy(self._handle)
+                capi.load_library().b2cnn_destroy(h)
             except Exception:
                 pass
-            self._handle = None
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:
+            pass
 
     def set_path(self, path: str):
         """'auto' | 'generic' (exact fp32 CUDA cores) | 'tensorcore' (tcgen05 conv1)."""

@@ -1,0 +1,134 @@
+"""Streaming replay at the model boundary (BASELINE.json configs[4]).
+
+The reference's live path is Kafka -> Spark -> ``write_to_mysql`` (bin/predictStream.py:53-192),
+which calls ``model(x_arr, a_arr)`` once per patient row with B=1.  None of that plumbing exists
+here (no Kafka / Spark / MySQL in this image, and it is out of scope); this module replays a WFDB
+numerics record through a *restatement of the window logic* and hands the whole micro-batch of
+windows to ONE ``predict()`` call -- the "batched GPU dispatch" the north-star asks for:
+
+  sendStream.py:39-72      one message per (sample, signal): value = [signal_index, sample];
+                           the index is the position in the record's selected signal list
+  processStream.py:196-208 per (patient, signal): mean over a 180 s window sliding by 5 s
+  processStream.py:62-123  forward-fill, back-fill, then 0-fill of the 5-second grid
+  predictStream.py:245-259 600 s windows sliding by 60 s  ->  120 points per signal
+  predictStream.py:105-139 x_arr[0, signal_index, :] = the 120 points; absent signals = zeros
+  predictStream.py:146-151 age from the patients table, 65.0 when unknown
+  predictStream.py:160-162,172-181  sigmoid -> RISK_SCORE row (SUBJECT_ID, PRED_TIME, RISK_SCORE)
+
+The reference's ``x_arr = np.empty(...)`` + stale ``signal_index`` quirk
+makes its live MySQL rows non-deterministic, so parity is asserted where it is defined: on
+identical ``x_arr`` at the ``model(x, a)`` boundary.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+# config.cfg:23 -- the names wfdb.rdrecord(channel_names=...) selects by (sendStream.py:46)
+CHANNEL_NAMES = ("HR", "RESP", "PULSE", "PVC Rate per Minute", "SpO2", "CVP", "ST V",
+                 "NBP Mean", "NBP Dias", "NBP Sys")
+N_CHANNELS = 10          # predictStream.py:105
+WINDOW_POINTS = 120      # config.cfg:23 WINDOWSIZE
+GRID_S = 5               # processStream.py: 5-second slide
+SMOOTH_S = 180           # processStream.py: 180-second window
+STRIDE_S = 60            # predictStream.py: 60-second slide
+
+
+@dataclass
+class NumericsRecord:
+    """A WFDB format-16 numerics record (little-endian int16, interleaved signals)."""
+    names: Tuple[str, ...]
+    gains: np.ndarray          # ADC units per physical unit
+    baselines: np.ndarray
+    fs: float                  # samples per second (1/60 for MIMIC numerics)
+    raw: np.ndarray            # [n_samples, n_signals] int16; -32768 == missing
+
+    @property
+    def physical(self) -> np.ndarray:
+        p = (self.raw.astype(np.float64) - self.baselines) / self.gains
+        p[self.raw == -32768] = np.nan
+        return p
+
+    @classmethod
+    def from_wfdb_files(cls, hea_path: str, dat_path: str) -> "NumericsRecord":
+        lines = [l.split() for l in open(hea_path).read().strip().splitlines() if not l.startswith("#")]
+        n_sig = int(lines[0][1])
+        fs = float(lines[0][2].split("/")[0])
+        names, gains, bases = [], [], []
+        for l in lines[1:1 + n_sig]:
+            g = l[2].split("/")[0]
+            gain = float(g.split("(")[0]) if g else 200.0
+            base = float(g.split("(")[1].rstrip(")")) if "(" in g else float(l[4])
+            names.append(" ".join(l[8:])); gains.append(gain or 200.0); bases.append(base)
+        raw = np.fromfile(dat_path, dtype="<i2").reshape(-1, n_sig)
+        return cls(tuple(names), np.array(gains), np.array(bases), fs, raw)
+
+
+def selected_signals(record: NumericsRecord) -> List[int]:
+    """Indices of the record's signals whose names are in CHANNEL_NAMES, in record order
+    (wfdb.rdrecord(channel_names=...), sendStream.py:46).  Message index i == position here."""
+    return [i for i, n in enumerate(record.names) if n in CHANNEL_NAMES]
+
+
+def smooth_to_grid(samples: np.ndarray, fs: float) -> np.ndarray:
+    """processStream.py:196-208 + :62-123 for one signal: value at grid time tau (multiples of 5 s)
+    = mean of the samples with time in (tau-180, tau]; NaN samples are skipped; then ffill, bfill,
+    0-fill."""
+    period = 1.0 / fs
+    t = np.arange(samples.shape[0]) * period
+    n_grid = int(np.floor(t[-1] / GRID_S)) + 1
+    tau = np.arange(n_grid) * GRID_S
+    lo = np.searchsorted(t, tau - SMOOTH_S, side="right")
+    hi = np.searchsorted(t, tau, side="right")
+    ok = ~np.isnan(samples)
+    csum = np.concatenate([[0.0], np.cumsum(np.where(ok, samples, 0.0))])
+    ccnt = np.concatenate([[0], np.cumsum(ok)])
+    cnt = ccnt[hi] - ccnt[lo]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        g = (csum[hi] - csum[lo]) / cnt
+    g[cnt == 0] = np.nan
+    idx = np.where(~np.isnan(g), np.arange(n_grid), -1)          # forward fill
+    np.maximum.accumulate(idx, out=idx)
+    g = np.where(idx >= 0, g[np.maximum(idx, 0)], np.nan)
+    if np.isnan(g).any():                                         # back fill, then zeros
+        good = np.where(~np.isnan(g))[0]
+        if good.size:
+            g[:good[0]] = g[good[0]]
+        g = np.nan_to_num(g, nan=0.0)
+    return g
+
+
+def assemble_windows(record: NumericsRecord) -> Tuple[np.ndarray, np.ndarray]:
+    """All model inputs of the replay: x_arr [n_windows, 10, 120] float64 (as predictStream.py:105
+    builds it) and the window start times in seconds."""
+    phys = record.physical
+    sel = selected_signals(record)
+    grids = [smooth_to_grid(phys[:, s], record.fs) for s in sel]
+    n_grid = min(len(g) for g in grids)
+    step = STRIDE_S // GRID_S
+    starts = np.arange(0, n_grid - WINDOW_POINTS + 1, step)
+    x = np.zeros((len(starts), N_CHANNELS, WINDOW_POINTS), dtype=np.float64)    # absent signals: zeros (:131)
+    for ch, g in enumerate(grids):                                              # message index == ch
+        x[:, ch, :] = np.lib.stride_tricks.sliding_window_view(g[:n_grid], WINDOW_POINTS)[starts]
+    return x, starts * float(GRID_S)
+
+
+def replay(model, record: NumericsRecord, subject_id: int, age: float = 65.0,
+           micro_batch: int = 0) -> List[Tuple[int, float, float]]:
+    """Score every window of the record and return the rows the reference INSERTs into
+    ``predictions`` (db/init.sql:24-28): (SUBJECT_ID, PRED_TIME [s since record start], RISK_SCORE).
+    ``micro_batch`` = windows per predict() call (0 = all at once); NaN scores are dropped
+    like predictStream.py:171."""
+    import torch
+    x, t0 = assemble_windows(record)
+    rows: List[Tuple[int, float, float]] = []
+    mb = micro_batch or len(x)
+    for b0 in range(0, len(x), mb):
+        xb = torch.from_numpy(x[b0:b0 + mb]).float()            # predictStream.py:155
+        prob = model.predict(xb, age, return_prob=True).cpu().numpy()
+        for tt, p in zip(t0[b0:b0 + mb], prob):
+            if not np.isnan(p):
+                rows.append((int(subject_id), float(tt), float(p)))
+    return rows
