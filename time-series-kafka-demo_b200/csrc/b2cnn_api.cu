@@ -390,6 +390,7 @@ extern "C" int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value)
         return B2CNN_OK;
     }
     if (!strcmp(key, "tc_fused")) { h->tc.opt_fused = value ? 1 : 0; return B2CNN_OK; }
+    if (!strcmp(key, "tc_variant")) { h->tc.opt_variant = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "profile")) { h->opt_profile = value ? 1 : 0; h->ev_valid = false; return B2CNN_OK; }
     if (!strcmp(key, "tc_splits")) {
         if (value != 2 && value != 3) return fail(B2CNN_EINVAL, "tc_splits must be 2 or 3");

@@ -264,6 +264,7 @@ __global__ void tc_compact_flags_kernel(int *flags, int B, int *list, int *count
 
 }  // namespace b2cnn
 #include "b2cnn_tc_fused.cuh"
+#include "b2cnn_tc_fused_ws.cuh"
 namespace b2cnn {
 
 // ------------------------------------------------------------------------------------------
@@ -558,15 +559,25 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     const size_t smem = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
                         FuBars::kTotal * 8 + 16;
     const int arch_id = d.K1 == 10 ? 0 : 1;
+    const size_t smem_ws = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
+                           WsBars::kTotal * 8 + 16;
+#define WS_LAUNCH(CC, SS, AA)                                                                          \
+    if (s.opt_variant == 0 && d.C == CC && s.splits == SS && arch_id == AA) {                          \
+        cudaError_t e = cudaFuncSetAttribute(tc_fused_ws_kernel<CC, SS, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws); \
+        if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }                             \
+        tc_fused_ws_kernel<CC, SS, AA><<<grid, kWsThreads, smem_ws, st>>>(tm, p);                      \
+    } else
 #define FU_LAUNCH(CC, SS, AA)                                                                          \
     if (d.C == CC && s.splits == SS && arch_id == AA) {                                                \
         cudaError_t e = cudaFuncSetAttribute(tc_fused_kernel<CC, SS, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }                             \
         tc_fused_kernel<CC, SS, AA><<<grid, kFuThreads, smem, st>>>(tm, p);                            \
     } else
+    WS_LAUNCH(3, 3, 0) WS_LAUNCH(3, 3, 1)
     FU_LAUNCH(3, 3, 0) FU_LAUNCH(3, 2, 0) FU_LAUNCH(2, 3, 0) FU_LAUNCH(1, 3, 0) FU_LAUNCH(3, 3, 1) FU_LAUNCH(2, 3, 1) FU_LAUNCH(1, 3, 1)
     { *err = "no fused instantiation for this channel count / split"; return -1; }
 #undef FU_LAUNCH
+#undef WS_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     int launches = 1 + staged;
