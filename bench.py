@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-windows", type=int, default=48, help="windows per worker process and step (reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc-variant", type=int, default=-1, help="experiment: force tensor-core epilogue variant 0/1")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -246,6 +247,8 @@ def main():
     x = tskd_b200.synth.make_windows(B, C, W, "normal", seed=1234 + rank, dtype=torch.bfloat16, device=dev)
     ages = tskd_b200.synth.make_ages(B, seed=1234 + rank, device=dev)
     model.set_profile(True)
+    if args.tc_variant >= 0:
+        model.set_option("tc_variant", args.tc_variant)
 
     def barrier():
         if world > 1:

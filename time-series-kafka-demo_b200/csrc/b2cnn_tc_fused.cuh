@@ -219,10 +219,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 4; ++i) { abuf[0][i][q2] = make_float2(0.f, 0.f); abuf[1][i][q2] = make_float2(0.f, 0.f); }
         }
-        uint32_t Dn[32];
+        // accumulator registers are double-buffered by step parity (block jj lives in Dbuf[jj & 1]; the
+        // next block's tcgen05.ld is issued into the other half) -- no register-to-register copies
+        uint32_t Dbuf[2][32];
         mbar_wait_parked(BAR(o_bar + FuBars::kTFull + 0), 0);
         tc_fence_after();
-        tmem_ld32_issue(tlane + 0, Dn);
+        tmem_ld32_issue(tlane + 0, Dbuf[0]);
         int n = 0, ti = 0;                                  // block-in-tile and tile index of block jj
 
         auto iteration = [&](int jj, auto doA_, auto doB_, auto par_) {
@@ -230,12 +232,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             constexpr int PAR = decltype(par_)::value;      // == jj & 1 (compile-time register naming)
             const int s = ti & 1;
             const int jb = jj - 1, m = jb >> 3, kk = jb & 7, u = m & 1;
-            float D[32];
             // ---------------- top: barriers ----------------
             if constexpr (doA) {
-                tmem_ld32_wait(Dn);
-#pragma unroll
-                for (int k = 0; k < 32; ++k) D[k] = __uint_as_float(Dn[k]);
+                tmem_ld32_wait(Dbuf[PAR]);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + (jj & 3)));
@@ -243,7 +242,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     const int s1 = (jj + 1) & 3;
                     mbar_wait_parked(BAR(o_bar + FuBars::kTFull + s1), ((jj + 1) >> 2) & 1);
                     tc_fence_after();
-                    tmem_ld32_issue(tlane + s1 * 32, Dn);
+                    tmem_ld32_issue(tlane + s1 * 32, Dbuf[PAR ^ 1]);
                 }
                 if (n == 0) mbar_wait_parked(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1);   // TMA bytes visible for the tap-9 reads
             }
@@ -256,6 +255,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // ---------------- middle: straight-line math ----------------
             float2 an[4][2];
             if constexpr (doA) {
+                auto Dv = [&](int idx) -> float { return __uint_as_float(Dbuf[PAR][idx]); };
                 if constexpr (ARCH == 0) {
                     const uint8_t *tile = sA_of(t, s, 0) + row * 128;
 #pragma unroll
@@ -268,16 +268,16 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
                     for (int q2 = 0; q2 < 2; ++q2) {
                         const int o0 = 2 * q2, o1 = 2 * q2 + 1;
-                        an[0][q2] = tanh_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, D[0 * 4 + o0]),
-                                                           max3_nan(pm6[q2].y, pm7[q2].y, D[0 * 4 + o1])), p.b1sp[q2]);
-                        an[1][q2] = tanh_fold2(make_float2(max3_nan(D[0 * 4 + o0], D[1 * 4 + o0], D[2 * 4 + o0]),
-                                                           max3_nan(D[0 * 4 + o1], D[1 * 4 + o1], D[2 * 4 + o1])), p.b1sp[q2]);
-                        an[2][q2] = tanh_fold2(make_float2(max3_nan(D[2 * 4 + o0], D[3 * 4 + o0], D[4 * 4 + o0]),
-                                                           max3_nan(D[2 * 4 + o1], D[3 * 4 + o1], D[4 * 4 + o1])), p.b1sp[q2]);
-                        an[3][q2] = tanh_fold2(make_float2(max3_nan(D[4 * 4 + o0], D[5 * 4 + o0], D[6 * 4 + o0]),
-                                                           max3_nan(D[4 * 4 + o1], D[5 * 4 + o1], D[6 * 4 + o1])), p.b1sp[q2]);
-                        pm6[q2] = make_float2(D[6 * 4 + o0], D[6 * 4 + o1]);
-                        pm7[q2] = make_float2(D[7 * 4 + o0], D[7 * 4 + o1]);
+                        an[0][q2] = tanh_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, Dv(0 * 4 + o0)),
+                                                           max3_nan(pm6[q2].y, pm7[q2].y, Dv(0 * 4 + o1))), p.b1sp[q2]);
+                        an[1][q2] = tanh_fold2(make_float2(max3_nan(Dv(0 * 4 + o0), Dv(1 * 4 + o0), Dv(2 * 4 + o0)),
+                                                           max3_nan(Dv(0 * 4 + o1), Dv(1 * 4 + o1), Dv(2 * 4 + o1))), p.b1sp[q2]);
+                        an[2][q2] = tanh_fold2(make_float2(max3_nan(Dv(2 * 4 + o0), Dv(3 * 4 + o0), Dv(4 * 4 + o0)),
+                                                           max3_nan(Dv(2 * 4 + o1), Dv(3 * 4 + o1), Dv(4 * 4 + o1))), p.b1sp[q2]);
+                        an[3][q2] = tanh_fold2(make_float2(max3_nan(Dv(4 * 4 + o0), Dv(5 * 4 + o0), Dv(6 * 4 + o0)),
+                                                           max3_nan(Dv(4 * 4 + o1), Dv(5 * 4 + o1), Dv(6 * 4 + o1))), p.b1sp[q2]);
+                        pm6[q2] = make_float2(Dv(6 * 4 + o0), Dv(6 * 4 + o1));
+                        pm7[q2] = make_float2(Dv(7 * 4 + o0), Dv(7 * 4 + o1));
                     }
                 } else {
                     // pool(2,2): pooled position 4j+i = max(pre[8j+2i], pre[8j+2i+1])
@@ -286,8 +286,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                         const int o0 = 2 * q2, o1 = 2 * q2 + 1;
 #pragma unroll
                         for (int i2 = 0; i2 < 4; ++i2)
-                            an[i2][q2] = tanh_fold2(make_float2(max_nan(D[(2 * i2) * 4 + o0], D[(2 * i2 + 1) * 4 + o0]),
-                                                                max_nan(D[(2 * i2) * 4 + o1], D[(2 * i2 + 1) * 4 + o1])), p.b1sp[q2]);
+                            an[i2][q2] = tanh_fold2(make_float2(max_nan(Dv((2 * i2) * 4 + o0), Dv((2 * i2 + 1) * 4 + o0)),
+                                                                max_nan(Dv((2 * i2) * 4 + o1), Dv((2 * i2 + 1) * 4 + o1))), p.b1sp[q2]);
                     }
                 }
             }
