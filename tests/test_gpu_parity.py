@@ -253,3 +253,29 @@ def test_full_size_properties():
     idx = torch.arange(0, B, B // 24, device=DEV)[:24]
     want = O.ref_independent(ref, x[idx].float().cpu(), ages[idx].cpu()).numpy()
     assert rel_err(y[idx].cpu().numpy(), want) <= TOL
+
+
+def test_single_launch_small_window_kernel(golden5):
+    """[1,10,120] (the production call, predictStream.py:157) runs as ONE kernel launch; it must
+    agree with the multi-kernel general path and with the reference goldens."""
+    g, sd = golden5
+    m = tskd_b200.B200MyCNN.from_reference(sd).to(DEV)
+    x = torch.from_numpy(g["xn"]).to(DEV)
+    a = torch.from_numpy(g["ab"]).to(DEV)
+    y_small = m.predict(x, a)
+    assert m.gpu_launches == 1 and m.last_path == "generic"
+    m.set_option("small_kernel", 0)
+    y_general = m.predict(x, a)
+    assert m.gpu_launches > 1
+    assert rel_err(y_small.cpu().numpy(), g["xn_ind_logits"]) <= 2e-6
+    assert rel_err(y_small.cpu().numpy(), y_general.cpu().numpy()) <= 2e-6
+    m.set_option("small_kernel", 1)
+    one = m(torch.from_numpy(g["x"]).to(DEV), torch.tensor([50.0], device=DEV))
+    assert m.gpu_launches == 1 and rel_err(one.cpu().numpy(), g["logit_age50"]) <= 2e-6
+    # bf16 input, other geometry, sigmoid epilogue
+    ref, m3 = _pair("mycnn3", 3, 1500)
+    xb = tskd_b200.synth.make_windows(40, 3, 1500, "physio", seed=2, dtype=torch.bfloat16)
+    ages = tskd_b200.synth.make_ages(40, seed=2)
+    want = torch.sigmoid(O.ref_independent(ref, xb.float(), ages)).numpy()
+    got = m3.predict(xb.to(DEV), ages.to(DEV), return_prob=True).cpu().numpy()
+    assert m3.gpu_launches == 1 and rel_err(got, want) <= TOL

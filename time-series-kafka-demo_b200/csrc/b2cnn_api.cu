@@ -44,6 +44,7 @@ struct b2cnn_handle {
     int64_t last_launches = 0;
     int last_path = 0;
     int64_t opt_profile = 0;
+    int64_t opt_small = 1;      // single-launch kernel for short windows / small batches
     cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};   // start, after front end, after head
     bool ev_valid = false;
     TcState tc;                 // tensor-core path state (b2cnn_tc.cu)
@@ -237,6 +238,15 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
             if (!h->ev_stage[i]) CU_TRY(cudaEventCreate(&h->ev_stage[i]));
         CU_TRY(cudaEventRecord(h->ev_stage[0], st));
     }
+    // short windows, few of them (the production call is [1,10,120]): one launch does everything
+    if (!tc && h->opt_small && (mode == B2CNN_MODE_INDEPENDENT || B == 1) && B <= 256 &&
+        (int64_t)d.C * d.W <= 8192 && small_supported(d)) {
+        int n1 = launch_small_forward(d, h->cw, h->hw, x, dtype, B, age, n_age, apply_sigmoid, out, st, &err);
+        if (n1 < 0) return fail(B2CNN_ECUDA, std::string("small-window kernel: ") + err);
+        if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[1], st)); CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }
+        h->last_launches = n1; h->last_path = B2CNN_PATH_GENERIC;
+        return B2CNN_OK;
+    }
     // feature layout: the generic kernel writes rows [B][L]; the tensor-core kernel's threads
     // are windows, so it writes the transpose [L][B] (coalesced across lanes).
     int64_t sB = d.L, sP = 1;
@@ -389,6 +399,7 @@ extern "C" int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value)
         h->opt_path = value;
         return B2CNN_OK;
     }
+    if (!strcmp(key, "small_kernel")) { h->opt_small = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "tc_fused")) { h->tc.opt_fused = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "tc_variant")) { h->tc.opt_variant = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "profile")) { h->opt_profile = value ? 1 : 0; h->ev_valid = false; return B2CNN_OK; }

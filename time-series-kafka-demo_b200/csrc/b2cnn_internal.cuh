@@ -102,6 +102,11 @@ int launch_lstm_head(const Dims &d, const HeadWeights &hw, const float *gates, i
 
 int choose_ksplit(int64_t B, int L, int num_sms);
 
+// b2cnn_small.cu: whole forward pass of short windows in one launch (independent windows only)
+bool small_supported(const Dims &d);
+int launch_small_forward(const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int dtype, int64_t B,
+                         const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
+
 void launch_transpose_wih(const float *wih0, float *wih0T, int L, cudaStream_t st);
 
 }  // namespace b2cnn
