@@ -239,7 +239,7 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
         CU_TRY(cudaEventRecord(h->ev_stage[0], st));
     }
     // short windows, few of them (the production call is [1,10,120]): one launch does everything
-    if (!tc && h->opt_small && (mode == B2CNN_MODE_INDEPENDENT || B == 1) && B <= 256 &&
+    if (h->opt_path != B2CNN_PATH_TENSORCORE && h->opt_small && (mode == B2CNN_MODE_INDEPENDENT || B == 1) && B <= 256 &&
         (int64_t)d.C * d.W <= 8192 && small_supported(d)) {
         int n1 = launch_small_forward(d, h->cw, h->hw, x, dtype, B, age, n_age, apply_sigmoid, out, st, &err);
         if (n1 < 0) return fail(B2CNN_ECUDA, std::string("small-window kernel: ") + err);

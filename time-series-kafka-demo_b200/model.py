@@ -104,7 +104,25 @@ class B200MyCNN(nn.Module):
                       self.affine2_scale.detach().float(), self.affine2_shift.detach().float()]
         return torch.cat(parts).contiguous()
 
+    # Weight changes reach the library lazily.  load_state_dict() and .to()/.cuda() mark the
+    # model dirty; after in-place edits of a parameter call sync_weights() (or any of the two).
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.__dict__["_dirty"] = True
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self.__dict__["_dirty"] = True
+        return r
+
+    def sync_weights(self):
+        self.__dict__["_dirty"] = True
+        self._ensure_handle()
+
     def _ensure_handle(self):
+        if not self.__dict__.get("_dirty", True) and self._handle is not None:
+            return self._lib, self._handle                      # fast path of the hot call
         dev = self._device()
         if dev.type != "cuda":
             if not torch.cuda.is_available():
@@ -113,6 +131,7 @@ class B200MyCNN(nn.Module):
             self.to("cuda")
             dev = self._device()
         lib = capi.load_library()
+        self.__dict__["_lib"] = lib
         if self._handle is None or self._handle_device != dev:
             self._release()
             cfg = capi.make_config(self.arch, dev.index if dev.index is not None else torch.cuda.current_device())
@@ -122,6 +141,7 @@ class B200MyCNN(nn.Module):
             capi.check(lib.b2cnn_set_option(h, b"tc_splits", int(self._tc_splits)), "b2cnn_set_option")
             capi.check(lib.b2cnn_set_option(h, b"path", _PATHS[self._path]), "b2cnn_set_option")
             self._synced_version = None
+            self.__dict__["_ws_need"] = {}
         if self._synced_version != self._weights_version():
             blob = self.packed_weights()
             with torch.cuda.device(dev):
@@ -130,6 +150,7 @@ class B200MyCNN(nn.Module):
                            "b2cnn_set_weights")
                 torch.cuda.current_stream().synchronize()
             self._synced_version = self._weights_version()
+        self.__dict__["_dirty"] = False
         return lib, self._handle
 
     def _release(self):
@@ -179,10 +200,14 @@ class B200MyCNN(nn.Module):
         return _PATH_NAMES.get(int(capi.load_library().b2cnn_last_path(self._handle)), "none")
 
     def _workspace(self, lib, h, B: int, mode: int, dev) -> torch.Tensor:
-        need = int(lib.b2cnn_workspace_bytes(h, B, mode))
-        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        return self._ws
+        cache = self.__dict__.setdefault("_ws_need", {})
+        need = cache.get((B, mode))
+        if need is None:
+            need = cache[(B, mode)] = int(lib.b2cnn_workspace_bytes(h, B, mode))
+        ws = self._ws
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return ws
 
     # ------------------------------------------------------------------ the hot call
     def _check_x(self, x: torch.Tensor) -> torch.Tensor:
@@ -194,30 +219,38 @@ class B200MyCNN(nn.Module):
 
     def _run(self, x: torch.Tensor, age: torch.Tensor, mode: int, sigmoid: bool) -> torch.Tensor:
         lib, h = self._ensure_handle()
-        dev = self._device()
+        dev = self._handle_device
         x = self._check_x(x)
         B = x.shape[0]
-        age = age.detach().reshape(-1).float().contiguous()
-        if age.numel() not in (1, B):
-            raise RuntimeError(f"age must have 1 or {B} elements, got {age.numel()}")
+        if not (age.dtype == torch.float32 and age.dim() == 1 and age.is_contiguous()):
+            age = age.detach().reshape(-1).float().contiguous()
+        n_age = age.numel()
+        if n_age != 1 and n_age != B:
+            raise RuntimeError(f"age must have 1 or {B} elements, got {n_age}")
         dtype = capi.DTYPE_BF16 if x.dtype == torch.bfloat16 else capi.DTYPE_F32
         if x.device.type == "cpu":
             # host buffers in, host buffers out: chunked H2D inside the library
             out = torch.empty(B, dtype=torch.float32)
             age_h = age.cpu()
             with torch.cuda.device(dev):
-                capi.check(lib.b2cnn_forward_host(h, x.data_ptr(), dtype, B, age_h.data_ptr(), age_h.numel(),
+                capi.check(lib.b2cnn_forward_host(h, x.data_ptr(), dtype, B, age_h.data_ptr(), n_age,
                                                   mode, int(sigmoid), out.data_ptr()), "b2cnn_forward_host")
             return out
         if x.device != dev:
             x = x.to(dev)
-        age = age.to(dev)
+        if age.device != dev:
+            age = age.to(dev)
         out = torch.empty(B, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            ws = self._workspace(lib, h, B, mode, dev)
-            st = torch.cuda.current_stream().cuda_stream
-            capi.check(lib.b2cnn_forward(h, x.data_ptr(), dtype, B, age.data_ptr(), age.numel(), mode, int(sigmoid),
-                                         out.data_ptr(), ws.data_ptr(), ws.numel(), st), "b2cnn_forward")
+        ws = self._workspace(lib, h, B, mode, dev)
+        if torch.cuda.current_device() == dev.index:            # the usual case: no device switch needed
+            rc = lib.b2cnn_forward(h, x.data_ptr(), dtype, B, age.data_ptr(), n_age, mode, int(sigmoid),
+                                   out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        else:
+            with torch.cuda.device(dev):
+                rc = lib.b2cnn_forward(h, x.data_ptr(), dtype, B, age.data_ptr(), n_age, mode, int(sigmoid),
+                                       out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        if rc:
+            capi.check(rc, "b2cnn_forward")
         return out
 
     @torch.no_grad()
