@@ -65,7 +65,8 @@ def test_replay_parity_gpu_vs_reference_scores():
     probs = np.array([r[2] for r in rows])
     assert rel_err(probs, g["probs"]) <= 1e-4                            # vs the unmodified reference
     rows_mb = S.replay(model, rec, subject_id=194, age=65.0, micro_batch=16)   # BATCHSIZE = 16 (config.cfg:26)
-    assert np.array_equal(np.array([r[2] for r in rows_mb]), probs)
+    # micro-batches of 16 take the single-launch small-window kernel, the full batch the general path
+    assert rel_err(np.array([r[2] for r in rows_mb]), probs) <= 1e-6
     # logits on identical x_arr: GPU vs golden vs oracle per-window loop
     x, _ = S.assemble_windows(rec)
     xt = torch.from_numpy(x).float()
