@@ -552,9 +552,14 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
             p.w9p[c][q2] = d.K1 == 10 ? make_float2(cw.w1[(c * d.K1 + 9) * kCMid + 2 * q2], cw.w1[(c * d.K1 + 9) * kCMid + 2 * q2 + 1])
                                       : make_float2(0.f, 0.f);
         p.b1sp[q2] = make_float2(cw.b1[2 * q2] * k2Log2e, cw.b1[2 * q2 + 1] * k2Log2e);
-        for (int k = 0; k < 5; ++k) p.w2p[q2][k] = make_float2(cw.w2[(2 * q2) * d.K2 + k], cw.w2[(2 * q2 + 1) * d.K2 + k]);
+        // conv2 consumes r = (1 - tanh)/2 of conv1: sum w*(1 - 2r) = sum(w) + sum (-2w)*r
+        for (int k = 0; k < 5; ++k) p.w2p[q2][k] = make_float2(-2.f * cw.w2[(2 * q2) * d.K2 + k], -2.f * cw.w2[(2 * q2 + 1) * d.K2 + k]);
     }
-    p.b2s = cw.b2 * k2Log2e;
+    {
+        double sw = 0.0;
+        for (int i = 0; i < kCMid * d.K2; ++i) sw += cw.w2[i];
+        p.b2s = (float)((cw.b2 + sw) * (double)k2Log2e);
+    }
     dim3 grid((unsigned)((B + 2 * kTcM - 1) / (2 * kTcM)), s.n_ranges);
     const size_t smem = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
                         FuBars::kTotal * 8 + 16;

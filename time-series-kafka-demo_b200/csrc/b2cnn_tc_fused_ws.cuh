@@ -212,13 +212,13 @@ tc_fused_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
                     for (int q2 = 0; q2 < 2; ++q2) {
                         const int o0 = 2 * q2, o1 = 2 * q2 + 1;
-                        an[0][q2] = tanh_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, D[0 * 4 + o0]),
+                        an[0][q2] = sig_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, D[0 * 4 + o0]),
                                                            max3_nan(pm6[q2].y, pm7[q2].y, D[0 * 4 + o1])), p.b1sp[q2]);
-                        an[1][q2] = tanh_fold2(make_float2(max3_nan(D[0 * 4 + o0], D[1 * 4 + o0], D[2 * 4 + o0]),
+                        an[1][q2] = sig_fold2(make_float2(max3_nan(D[0 * 4 + o0], D[1 * 4 + o0], D[2 * 4 + o0]),
                                                            max3_nan(D[0 * 4 + o1], D[1 * 4 + o1], D[2 * 4 + o1])), p.b1sp[q2]);
-                        an[2][q2] = tanh_fold2(make_float2(max3_nan(D[2 * 4 + o0], D[3 * 4 + o0], D[4 * 4 + o0]),
+                        an[2][q2] = sig_fold2(make_float2(max3_nan(D[2 * 4 + o0], D[3 * 4 + o0], D[4 * 4 + o0]),
                                                            max3_nan(D[2 * 4 + o1], D[3 * 4 + o1], D[4 * 4 + o1])), p.b1sp[q2]);
-                        an[3][q2] = tanh_fold2(make_float2(max3_nan(D[4 * 4 + o0], D[5 * 4 + o0], D[6 * 4 + o0]),
+                        an[3][q2] = sig_fold2(make_float2(max3_nan(D[4 * 4 + o0], D[5 * 4 + o0], D[6 * 4 + o0]),
                                                            max3_nan(D[4 * 4 + o1], D[5 * 4 + o1], D[6 * 4 + o1])), p.b1sp[q2]);
                         pm6[q2] = make_float2(D[6 * 4 + o0], D[6 * 4 + o1]);
                         pm7[q2] = make_float2(D[7 * 4 + o0], D[7 * 4 + o1]);
@@ -229,7 +229,7 @@ tc_fused_ws_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         const int o0 = 2 * q2, o1 = 2 * q2 + 1;
 #pragma unroll
                         for (int i2 = 0; i2 < 4; ++i2)
-                            an[i2][q2] = tanh_fold2(make_float2(max_nan(D[(2 * i2) * 4 + o0], D[(2 * i2 + 1) * 4 + o0]),
+                            an[i2][q2] = sig_fold2(make_float2(max_nan(D[(2 * i2) * 4 + o0], D[(2 * i2 + 1) * 4 + o0]),
                                                                 max_nan(D[(2 * i2) * 4 + o1], D[(2 * i2 + 1) * 4 + o1])), p.b1sp[q2]);
                     }
                 }

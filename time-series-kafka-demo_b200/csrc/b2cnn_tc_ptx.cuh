@@ -212,6 +212,18 @@ __device__ __forceinline__ float2 tanh_fold2(float2 m, float2 bias_scaled) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
     return fma2(make_float2(r0, r1), make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
 }
+// r = 1 / (1 + 2^(2 log2e (m + bias))) for two values: tanh(m + bias) == 1 - 2 r.  conv2 consumes r
+// directly (its weights are pre-multiplied by -2 and its bias absorbs sum(w)), saving the final FMA.
+__device__ __forceinline__ float2 sig_fold2(float2 m, float2 bias_scaled) {
+    const float2 a = fma2(m, make_float2(k2Log2e, k2Log2e), bias_scaled);
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a.y));
+    const float2 d = add2(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+    return make_float2(r0, r1);
+}
 constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
