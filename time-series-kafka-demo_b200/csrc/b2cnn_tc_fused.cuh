@@ -219,76 +219,37 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 4; ++i) { abuf[0][i][q2] = make_float2(0.f, 0.f); abuf[1][i][q2] = make_float2(0.f, 0.f); }
         }
-        // One accumulator register set: the pre-activations are consumed by the pooling maxima at the
-        // top of stage A, so the next block's tcgen05.ld is issued into the same registers right
-        // after and completes under the rest of the iteration.  The epilogue constants live in
-        // registers for the whole stream (no per-step constant-bank reloads).
-        uint32_t Dr[32];
+        // accumulator registers are double-buffered by step parity (block jj lives in Dbuf[jj & 1]; the
+        // next block's tcgen05.ld is issued into the other half) -- no register-to-register copies
+        uint32_t Dbuf[2][32];
         mbar_wait_parked(BAR(o_bar + FuBars::kTFull + 0), 0);
         tc_fence_after();
-        tmem_ld32_issue(tlane + 0, Dr);
+        tmem_ld32_issue(tlane + 0, Dbuf[0]);
         int n = 0, ti = 0;                                  // block-in-tile and tile index of block jj
-        float2 w2r[2][5], w9r[C][2], b1r[2];
+        float2 w2r[2][5];                                   // conv2 weights stay in registers for the whole stream
 #pragma unroll
-        for (int q2 = 0; q2 < 2; ++q2) {
-            b1r[q2] = p.b1sp[q2];
+        for (int q2 = 0; q2 < 2; ++q2)
 #pragma unroll
             for (int k = 0; k < 5; ++k) w2r[q2][k] = p.w2p[q2][k];
-#pragma unroll
-            for (int c = 0; c < C; ++c) w9r[c][q2] = p.w9p[c][q2];
-        }
-        const float2 b2r = make_float2(p.b2s, p.b2s);
 
         auto iteration = [&](int jj, auto doA_, auto doB_, auto par_) {
             constexpr bool doA = decltype(doA_)::value, doB = decltype(doB_)::value;
             constexpr int PAR = decltype(par_)::value;      // == jj & 1 (compile-time register naming)
             const int s = ti & 1;
             const int jb = jj - 1, m = jb >> 3, kk = jb & 7, u = m & 1;
-            auto Dv = [&](int idx) -> float { return __uint_as_float(Dr[idx]); };
-            float2 M[4][2];                                  // pooled pre-activations of block jj
-            // ---------------- top: barriers, pooling maxima, next block's load ----------------
+            // ---------------- top: barriers ----------------
             if constexpr (doA) {
-                tmem_ld32_wait(Dr);
+                tmem_ld32_wait(Dbuf[PAR]);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + (jj & 3)));
-                if constexpr (ARCH == 0) {
-                    if (n == 0) mbar_wait_parked(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1);   // TMA bytes visible for the tap-9 reads
-                    const uint8_t *tile = sA_of(t, s, 0) + row * 128;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
-                        const float xv = __uint_as_float((uint32_t)raw << 16);
-#pragma unroll
-                        for (int q2 = 0; q2 < 2; ++q2) pm7[q2] = fma2(w9r[c][q2], make_float2(xv, xv), pm7[q2]);
-                    }
-#pragma unroll
-                    for (int q2 = 0; q2 < 2; ++q2) {
-                        const int o0 = 2 * q2, o1 = 2 * q2 + 1;
-                        M[0][q2] = make_float2(max3_nan(pm6[q2].x, pm7[q2].x, Dv(0 * 4 + o0)), max3_nan(pm6[q2].y, pm7[q2].y, Dv(0 * 4 + o1)));
-                        M[1][q2] = make_float2(max3_nan(Dv(0 * 4 + o0), Dv(1 * 4 + o0), Dv(2 * 4 + o0)), max3_nan(Dv(0 * 4 + o1), Dv(1 * 4 + o1), Dv(2 * 4 + o1)));
-                        M[2][q2] = make_float2(max3_nan(Dv(2 * 4 + o0), Dv(3 * 4 + o0), Dv(4 * 4 + o0)), max3_nan(Dv(2 * 4 + o1), Dv(3 * 4 + o1), Dv(4 * 4 + o1)));
-                        M[3][q2] = make_float2(max3_nan(Dv(4 * 4 + o0), Dv(5 * 4 + o0), Dv(6 * 4 + o0)), max3_nan(Dv(4 * 4 + o1), Dv(5 * 4 + o1), Dv(6 * 4 + o1)));
-                        pm6[q2] = make_float2(Dv(6 * 4 + o0), Dv(6 * 4 + o1));
-                        pm7[q2] = make_float2(Dv(7 * 4 + o0), Dv(7 * 4 + o1));
-                    }
-                } else {
-                    // pool(2,2): pooled position 4j+i = max(pre[8j+2i], pre[8j+2i+1])
-#pragma unroll
-                    for (int q2 = 0; q2 < 2; ++q2) {
-                        const int o0 = 2 * q2, o1 = 2 * q2 + 1;
-#pragma unroll
-                        for (int i2 = 0; i2 < 4; ++i2)
-                            M[i2][q2] = make_float2(max_nan(Dv((2 * i2) * 4 + o0), Dv((2 * i2 + 1) * 4 + o0)),
-                                                    max_nan(Dv((2 * i2) * 4 + o1), Dv((2 * i2 + 1) * 4 + o1)));
-                    }
-                }
-                if (jj + 1 < J) {                           // the accumulator registers are free again
+                if (jj + 1 < J) {                           // prefetch the next block's accumulators
                     const int s1 = (jj + 1) & 3;
                     mbar_wait_parked(BAR(o_bar + FuBars::kTFull + s1), ((jj + 1) >> 2) & 1);
                     tc_fence_after();
-                    tmem_ld32_issue(tlane + s1 * 32, Dr);
+                    tmem_ld32_issue(tlane + s1 * 32, Dbuf[PAR ^ 1]);
                 }
+                if (n == 0) mbar_wait_parked(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1);   // TMA bytes visible for the tap-9 reads
             }
             if constexpr (doB) {
                 if (kk == 0) {                              // first store of chunk m into A buffer u
@@ -299,19 +260,50 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // ---------------- middle: straight-line math ----------------
             float2 an[4][2];
             if constexpr (doA) {
+                auto Dv = [&](int idx) -> float { return __uint_as_float(Dbuf[PAR][idx]); };
+                if constexpr (ARCH == 0) {
+                    const uint8_t *tile = sA_of(t, s, 0) + row * 128;
 #pragma unroll
-                for (int q2 = 0; q2 < 2; ++q2)
+                    for (int c = 0; c < C; ++c) {
+                        const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
+                        const float xv = __uint_as_float((uint32_t)raw << 16);
 #pragma unroll
-                    for (int i2 = 0; i2 < 4; ++i2) an[i2][q2] = sig_fold2(M[i2][q2], b1r[q2]);   // r = (1 - tanh) / 2
+                        for (int q2 = 0; q2 < 2; ++q2) pm7[q2] = fma2(p.w9p[c][q2], make_float2(xv, xv), pm7[q2]);
+                    }
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) {
+                        const int o0 = 2 * q2, o1 = 2 * q2 + 1;
+                        an[0][q2] = sig_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, Dv(0 * 4 + o0)),
+                                                           max3_nan(pm6[q2].y, pm7[q2].y, Dv(0 * 4 + o1))), p.b1sp[q2]);
+                        an[1][q2] = sig_fold2(make_float2(max3_nan(Dv(0 * 4 + o0), Dv(1 * 4 + o0), Dv(2 * 4 + o0)),
+                                                           max3_nan(Dv(0 * 4 + o1), Dv(1 * 4 + o1), Dv(2 * 4 + o1))), p.b1sp[q2]);
+                        an[2][q2] = sig_fold2(make_float2(max3_nan(Dv(2 * 4 + o0), Dv(3 * 4 + o0), Dv(4 * 4 + o0)),
+                                                           max3_nan(Dv(2 * 4 + o1), Dv(3 * 4 + o1), Dv(4 * 4 + o1))), p.b1sp[q2]);
+                        an[3][q2] = sig_fold2(make_float2(max3_nan(Dv(4 * 4 + o0), Dv(5 * 4 + o0), Dv(6 * 4 + o0)),
+                                                           max3_nan(Dv(4 * 4 + o1), Dv(5 * 4 + o1), Dv(6 * 4 + o1))), p.b1sp[q2]);
+                        pm6[q2] = make_float2(Dv(6 * 4 + o0), Dv(6 * 4 + o1));
+                        pm7[q2] = make_float2(Dv(7 * 4 + o0), Dv(7 * 4 + o1));
+                    }
+                } else {
+                    // pool(2,2): pooled position 4j+i = max(pre[8j+2i], pre[8j+2i+1])
+#pragma unroll
+                    for (int q2 = 0; q2 < 2; ++q2) {
+                        const int o0 = 2 * q2, o1 = 2 * q2 + 1;
+#pragma unroll
+                        for (int i2 = 0; i2 < 4; ++i2)
+                            an[i2][q2] = sig_fold2(make_float2(max_nan(Dv((2 * i2) * 4 + o0), Dv((2 * i2 + 1) * 4 + o0)),
+                                                                max_nan(Dv((2 * i2) * 4 + o1), Dv((2 * i2 + 1) * 4 + o1))), p.b1sp[q2]);
+                    }
+                }
             }
             if constexpr (doB) {
-                // conv2 on r (weights pre-multiplied by -2, bias absorbs sum(w)): 40 FFMA2
+                // conv2 on r = (1 - tanh)/2 (weights pre-multiplied by -2, bias absorbs sum(w)): 40 FFMA2
                 float2 acc[4][2];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
 #pragma unroll
                 for (int q2 = 0; q2 < 2; ++q2) {
-                    // r(step jb-1) = abuf[PAR], r(step jb) = abuf[PAR ^ 1]
+                    // a1(step jb-1) = abuf[PAR], a1(step jb) = abuf[PAR ^ 1]
                     const float2 A8[8] = {abuf[PAR][0][q2], abuf[PAR][1][q2], abuf[PAR][2][q2], abuf[PAR][3][q2],
                                           abuf[PAR ^ 1][0][q2], abuf[PAR ^ 1][1][q2], abuf[PAR ^ 1][2][q2], abuf[PAR ^ 1][3][q2]};
 #pragma unroll
@@ -327,10 +319,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
                 float2 f;                                                    // features 2*jb-FOFF, 2*jb-FOFF+1
                 if constexpr (ARCH == 0) {
-                    f = tanh_fold2(make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3])), b2r);
+                    f = tanh_fold2(make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3])), make_float2(p.b2s, p.b2s));
                     c2c = c2[3];
                 } else {
-                    f = tanh_fold2(make_float2(max_nan(c2[0], c2[1]), max_nan(c2[2], c2[3])), b2r);
+                    f = tanh_fold2(make_float2(max_nan(c2[0], c2[1]), max_nan(c2[2], c2[3])), make_float2(p.b2s, p.b2s));
                 }
                 nan_probe = fma2(f, make_float2(0.f, 0.f), nan_probe);
                 // three bf16 pieces of (f0, f1) -> column kk of this lane's row of the A operand
@@ -344,7 +336,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 tmem_st1(acol + 8, md);
                 tmem_st1(acol + 16, lo);
             }
-            if constexpr (doA) {                            // r(block jj) replaces r(block jj-2)
+            if constexpr (doA) {                            // a1(block jj) replaces a1(block jj-2)
 #pragma unroll
                 for (int q2 = 0; q2 < 2; ++q2)
 #pragma unroll
