@@ -164,8 +164,9 @@ def test_tc_epilogue_variants_agree(kind):
     x = tskd_b200.synth.make_windows(333, 3, 7504, "physio", seed=51, dtype=torch.bfloat16).to(DEV)
     ages = tskd_b200.synth.make_ages(333, seed=51).to(DEV)
     y0 = m.predict(x, ages)
-    m.set_option("tc_variant", 0)
-    y1 = m.predict(x, ages)
-    assert m.last_path == "tensorcore" and torch.equal(y0, y1)
+    for variant in (0, 2):                  # 0: warp-specialised A/B epilogue; 2: three window tiles per SM
+        m.set_option("tc_variant", variant)
+        y1 = m.predict(x, ages)
+        assert m.last_path == "tensorcore" and torch.equal(y0, y1), variant
     want = O.ref_independent(ref, x.float().cpu(), ages.cpu()).numpy()
     assert rel_err(y0.cpu().numpy(), want) <= TOL

@@ -401,7 +401,11 @@ extern "C" int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value)
     }
     if (!strcmp(key, "small_kernel")) { h->opt_small = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "tc_fused")) { h->tc.opt_fused = value ? 1 : 0; return B2CNN_OK; }
-    if (!strcmp(key, "tc_variant")) { h->tc.opt_variant = value ? 1 : 0; return B2CNN_OK; }
+    if (!strcmp(key, "tc_variant")) {
+        if (value < 0 || value > 2) return fail(B2CNN_EINVAL, "tc_variant must be 0, 1 or 2");
+        h->tc.opt_variant = value;
+        return B2CNN_OK;
+    }
     if (!strcmp(key, "profile")) { h->opt_profile = value ? 1 : 0; h->ev_valid = false; return B2CNN_OK; }
     if (!strcmp(key, "tc_splits")) {
         if (value != 2 && value != 3) return fail(B2CNN_EINVAL, "tc_splits must be 2 or 3");

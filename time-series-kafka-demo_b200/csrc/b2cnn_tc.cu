@@ -265,6 +265,7 @@ __global__ void tc_compact_flags_kernel(int *flags, int B, int *list, int *count
 }  // namespace b2cnn
 #include "b2cnn_tc_fused.cuh"
 #include "b2cnn_tc_fused_ws.cuh"
+#include "b2cnn_tc_fused3.cuh"
 namespace b2cnn {
 
 // ------------------------------------------------------------------------------------------
@@ -564,6 +565,23 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     const size_t smem = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
                         FuBars::kTotal * 8 + 16;
     const int arch_id = d.K1 == 10 ? 0 : 1;
+    if (s.opt_variant == 2 && d.C == 3 && s.splits == 3) {          // three window tiles per SM
+        dim3 grid3((unsigned)((B + kF3Tiles * kTcM - 1) / (kF3Tiles * kTcM)), s.n_ranges);
+        const size_t smem3 = (size_t)kF3Tiles * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
+                             F3Bars::kTotal * 8 + 16;
+        uint32_t stagger = 900;
+        if (const char *e = getenv("B2CNN_TC_STAGGER_NS")) stagger = (uint32_t)atoi(e);
+        cudaError_t e3;
+        if (arch_id == 0) {
+            e3 = cudaFuncSetAttribute(tc_fused3_kernel<3, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+            if (e3 == cudaSuccess) tc_fused3_kernel<3, 3, 0><<<grid3, kF3Threads, smem3, st>>>(tm, p, stagger);
+        } else {
+            e3 = cudaFuncSetAttribute(tc_fused3_kernel<3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+            if (e3 == cudaSuccess) tc_fused3_kernel<3, 3, 1><<<grid3, kF3Threads, smem3, st>>>(tm, p, stagger);
+        }
+        if (e3 != cudaSuccess) { *err = cudaGetErrorString(e3); return -1; }
+    } else
+    {
     const size_t smem_ws = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
                            WsBars::kTotal * 8 + 16;
 #define WS_LAUNCH(CC, SS, AA)                                                                          \
@@ -583,6 +601,7 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     { *err = "no fused instantiation for this channel count / split"; return -1; }
 #undef FU_LAUNCH
 #undef WS_LAUNCH
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     int launches = 1 + staged;

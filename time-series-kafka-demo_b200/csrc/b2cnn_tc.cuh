@@ -13,7 +13,7 @@ struct TcState {
     bool has_v1 = false;         // tc_frontend_kernel (features out) exists for this geometry (MyCNN5 only)
     bool fused_ready = false;    // fused conv + projection kernel usable (C <= 3)
     int64_t opt_fused = 1;
-    int64_t opt_variant = 1;     // 1 = tc_fused_kernel (default, faster); 0 = warp-specialised epilogue (tc_fused_ws_kernel)
+    int64_t opt_variant = 1;     // 1 = tc_fused_kernel (2 window tiles/SM); 0 = warp-specialised epilogue; 2 = tc_fused3_kernel (3 tiles/SM)
 };
 
 const char *tc_error();
