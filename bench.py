@@ -340,7 +340,7 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # committed ncu captures under profiles/ (None until a capture exists for that path).
 TRAFFIC = {"generic": 1.846642e9 + 0.297926e9,      # profiles/r01_generic_frontend_ncu_full.txt (features written to HBM)
-           "tensorcore": 1.945067e9 + 0.034012e9}   # profiles/r01_fused_fused_ncu_full.txt (halo re-reads + gate partials)
+           "tensorcore": 1.944909e9 + 0.033627e9}   # profiles/r01_final_fused_ncu_full.txt (halo re-reads + gate partials)
 
 if __name__ == "__main__":
     main()
