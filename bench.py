@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-windows", type=int, default=48, help="windows per worker process and step (reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tc-variant", type=int, default=-1, help="experiment: force tensor-core epilogue variant 0/1")
+    ap.add_argument("--tc-splits", type=int, default=3, help="bf16 pieces per fp32 conv1 weight on the tensor cores (3 = fp32-equivalent)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -241,14 +241,12 @@ def main():
     B = args.batch
     arch = tskd_b200.ARCH_PRESETS[KIND].with_shape(C, W)
     torch.manual_seed(0 if rank == 0 else 1000 + rank)     # only rank 0's weights survive
-    model = tskd_b200.B200MyCNN(arch, path=args.path).to(dev)
+    model = tskd_b200.B200MyCNN(arch, path=args.path, tc_splits=args.tc_splits).to(dev)
     if world > 1:
         broadcast_weights(model, src=0)                    # the one init-time NCCL collective
     x = tskd_b200.synth.make_windows(B, C, W, "normal", seed=1234 + rank, dtype=torch.bfloat16, device=dev)
     ages = tskd_b200.synth.make_ages(B, seed=1234 + rank, device=dev)
     model.set_profile(True)
-    if args.tc_variant >= 0:
-        model.set_option("tc_variant", args.tc_variant)
 
     def barrier():
         if world > 1:

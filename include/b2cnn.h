@@ -105,7 +105,8 @@ int b2cnn_forward_host(b2cnn_handle *h, const void *x_host, int dtype, int64_t B
 int b2cnn_features(b2cnn_handle *h, const void *x, int dtype, int64_t B, float *feats,
                    void *stream);
 
-/* Options: "path" = B2CNN_PATH_*; "tc_splits" = 2|3 (bf16 pieces per fp32 conv1 weight);
+/* Options: "path" = B2CNN_PATH_*; "tc_splits" = 2|3: bf16 pieces per fp32 conv1 weight on the
+ * tensor cores (3, default: exact fp32 weights; 2: weights rounded to 16 mantissa bits);
  * "profile" = 0|1: record CUDA events around the stages of each b2cnn_forward on its stream. */
 int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value);
 int64_t b2cnn_get_option(b2cnn_handle *h, const char *key);

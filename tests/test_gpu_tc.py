@@ -65,12 +65,17 @@ def test_tc_matches_generic_kernel():
 
 
 def test_tc_two_piece_weights_still_inside_tolerance():
+    """tc_splits=2 keeps 16 mantissa bits of every conv1 weight (6 instead of 9 MMAs per block): an option, not the
+    default; logits stay well inside the north-star tolerance but are no longer fp32-equivalent."""
     ref, m2 = _pair(3, 7504, tc_splits=2)
-    x = tskd_b200.synth.make_windows(128, 3, 7504, "normal", seed=12, dtype=torch.bfloat16)
-    ages = tskd_b200.synth.make_ages(128, seed=12)
+    _, m3 = _pair(3, 7504, tc_splits=3)
+    x = tskd_b200.synth.make_windows(300, 3, 7504, "physio", seed=12, dtype=torch.bfloat16)
+    ages = tskd_b200.synth.make_ages(300, seed=12)
     want = O.ref_independent(ref, x.float(), ages).numpy()
-    got = m2.predict(x.to(DEV), ages.to(DEV)).cpu().numpy()
-    assert m2.last_path == "tensorcore" and rel_err(got, want) <= TOL
+    got2 = m2.predict(x.to(DEV), ages.to(DEV)).cpu().numpy()
+    got3 = m3.predict(x.to(DEV), ages.to(DEV)).cpu().numpy()
+    assert m2.last_path == "tensorcore" and rel_err(got2, want) <= TOL
+    assert rel_err(got3, want) <= rel_err(got2, want) + 1e-7
 
 
 def test_tc_nan_inf_windows_are_recomputed_exactly():
@@ -154,19 +159,3 @@ def test_tc_fused_prefix_and_permutation_consistency():
     assert torch.equal(m.predict(x[:300], ages[:300]), y[:300])
     perm = torch.randperm(700, device=DEV)
     assert torch.equal(m.predict(x[perm], ages[perm]), y[perm])
-
-
-@pytest.mark.parametrize("kind", ["mycnn5", "mycnn3"])
-def test_tc_epilogue_variants_agree(kind):
-    """tc_variant 1 (default: one thread streams a window) and 0 (warp-specialised A/B epilogue) run the same
-    arithmetic in the same order: bit-identical logits."""
-    ref, m = _pair(3, 7504, kind=kind)
-    x = tskd_b200.synth.make_windows(333, 3, 7504, "physio", seed=51, dtype=torch.bfloat16).to(DEV)
-    ages = tskd_b200.synth.make_ages(333, seed=51).to(DEV)
-    y0 = m.predict(x, ages)
-    for variant in (0, 2):                  # 0: warp-specialised A/B epilogue; 2: three window tiles per SM
-        m.set_option("tc_variant", variant)
-        y1 = m.predict(x, ages)
-        assert m.last_path == "tensorcore" and torch.equal(y0, y1), variant
-    want = O.ref_independent(ref, x.float().cpu(), ages.cpu()).numpy()
-    assert rel_err(y0.cpu().numpy(), want) <= TOL

@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libb2cnn.so")
+# B2CNN_LIB: experiment hook (scripts/build_ablations.sh builds instrumented copies of the same library)
+_LIB_PATH = os.environ.get("B2CNN_LIB") or os.path.join(_HERE, "lib", "libb2cnn.so")
 
 OK, EINVAL, EARCH, EVIEW, ECUDA, ESTATE = range(6)
 DTYPE_F32, DTYPE_BF16 = 0, 1

@@ -40,7 +40,7 @@ struct b2cnn_handle {
     float *d_wih0T = nullptr;   // [L][64]
     int64_t n_weights = 0;
     int64_t opt_path = B2CNN_PATH_AUTO;
-    int64_t opt_tc_splits = 3;
+    int64_t opt_tc_splits = 3;   // bf16 pieces per conv1 weight in the fused kernels
     int64_t last_launches = 0;
     int last_path = 0;
     int64_t opt_profile = 0;
@@ -401,11 +401,6 @@ extern "C" int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value)
     }
     if (!strcmp(key, "small_kernel")) { h->opt_small = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "tc_fused")) { h->tc.opt_fused = value ? 1 : 0; return B2CNN_OK; }
-    if (!strcmp(key, "tc_variant")) {
-        if (value < 0 || value > 2) return fail(B2CNN_EINVAL, "tc_variant must be 0, 1 or 2");
-        h->tc.opt_variant = value;
-        return B2CNN_OK;
-    }
     if (!strcmp(key, "profile")) { h->opt_profile = value ? 1 : 0; h->ev_valid = false; return B2CNN_OK; }
     if (!strcmp(key, "tc_splits")) {
         if (value != 2 && value != 3) return fail(B2CNN_EINVAL, "tc_splits must be 2 or 3");

@@ -264,8 +264,6 @@ __global__ void tc_compact_flags_kernel(int *flags, int B, int *list, int *count
 
 }  // namespace b2cnn
 #include "b2cnn_tc_fused.cuh"
-#include "b2cnn_tc_fused_ws.cuh"
-#include "b2cnn_tc_fused3.cuh"
 namespace b2cnn {
 
 // ------------------------------------------------------------------------------------------
@@ -320,8 +318,13 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
     if (!arch_ok(d) && !arch1_ok(d)) return 0;   // not an error: this shape takes the generic path
     if (!get_encode()) return 0;
     // band matrices: piece sp of T_c[k][(s,o)] = w1[o][c][k-s], stored as UMMA K-major
-    // no-swizzle core matrices: byte = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2, n = s*4+o
-    std::vector<uint16_t> host((size_t)d.C * splits * 512, 0);
+    // no-swizzle core matrices: byte = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2, n = s*4+o.
+    //   d_bmats   [C][3][1 KB]  three bf16 pieces (hi/mid/lo: the full 24-bit fp32 mantissa)
+    //   d_bmats2  [C][2][1 KB]  the first two pieces only (16 mantissa bits; tc_splits=2, an option:
+    //                           6 instead of 9 MMAs per block, weights rounded to 2^-17 relative)
+    // (A mixed-format MMA -- bf16 samples x fp16 weight pieces, 22 bits in two pieces -- was tried:
+    //  kind::f16 with a_format != b_format raises "illegal instruction" on sm_100a.)
+    std::vector<uint16_t> host((size_t)d.C * 3 * 512, 0), host2((size_t)d.C * 2 * 512, 0);
     for (int c = 0; c < d.C; ++c)
         for (int sft = 0; sft < 8; ++sft)
             for (int o = 0; o < kCMid; ++o)
@@ -331,14 +334,17 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
                     float w = cw.w1[(c * d.K1 + tap) * kCMid + o];
                     const int n = sft * 4 + o;
                     const size_t off = (size_t)(n / 8) * 128 + (k / 8) * 64 + (n % 8) * 8 + (k % 8);   // in bf16 units
-                    for (int sp = 0; sp < splits; ++sp) {
+                    for (int sp = 0; sp < 3; ++sp) {
                         const uint16_t piece = bf16_rn(w);
-                        host[((size_t)c * splits + sp) * 512 + off] = piece;
+                        host[((size_t)c * 3 + sp) * 512 + off] = piece;
+                        if (sp < 2) host2[((size_t)c * 2 + sp) * 512 + off] = piece;
                         w -= bf16_to_f(piece);
                     }
                 }
     if (!s.d_bmats && cudaMalloc(&s.d_bmats, host.size() * 2 + 16) != cudaSuccess) { g_tc_err = "cudaMalloc(band matrices)"; return -1; }
+    if (!s.d_bmats2 && cudaMalloc(&s.d_bmats2, host2.size() * 2 + 16) != cudaSuccess) { g_tc_err = "cudaMalloc(band matrices)"; return -1; }
     if (cudaMemcpyAsync(s.d_bmats, host.data(), host.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(s.d_bmats2, host2.data(), host2.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) { g_tc_err = "upload band matrices"; return -1; }
     s.ready = true;
     s.has_v1 = arch_ok(d);
@@ -363,8 +369,10 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
 
 void tc_release(TcState &s) {
     cudaFree(s.d_bmats);
+    cudaFree(s.d_bmats2);
     cudaFree(s.d_wpack);
     s.d_bmats = nullptr;
+    s.d_bmats2 = nullptr;
     s.d_wpack = nullptr;
     s.ready = s.fused_ready = false;
 }
@@ -464,15 +472,15 @@ static int launch_tc_kernel(const TcState &s, const Dims &d, const ConvWeights &
     p.b2s = cw.b2 * k2Log2e;
     const int n_pr = (d.L + p.feats_per_cta - 1) / p.feats_per_cta;
     dim3 grid((unsigned)((B + kTcM - 1) / kTcM), n_pr);
-    const size_t smem = (size_t)2 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 256 + 1024;
+    const size_t smem = (size_t)2 * d.C * kTcABytes + (size_t)d.C * 3 * kTcBBytes + 256 + 1024;
 #define TC_LAUNCH(CC, SS)                                                                              \
-    if (d.C == CC && s.splits == SS) {                                                                 \
+    if (d.C == CC) {                                                                 \
         cudaError_t e = cudaFuncSetAttribute(tc_frontend_kernel<CC, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }                             \
         tc_frontend_kernel<CC, SS><<<grid, kTcThreads, smem, st>>>(tm, p);                             \
     } else
-    TC_LAUNCH(3, 3) TC_LAUNCH(3, 2) TC_LAUNCH(1, 3) TC_LAUNCH(2, 3) TC_LAUNCH(4, 3) TC_LAUNCH(4, 2)
-    { *err = "no tensor-core instantiation for this channel count / split"; return -1; }
+    TC_LAUNCH(3, 3) TC_LAUNCH(1, 3) TC_LAUNCH(2, 3) TC_LAUNCH(4, 3)
+    { *err = "no tensor-core instantiation for this channel count"; return -1; }
 #undef TC_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
@@ -544,7 +552,6 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     TcFusedParams p;
     memset(&p, 0, sizeof p);
     p.partial = partial; p.nanflag = flags;
-    p.bmats = reinterpret_cast<const uint8_t *>(s.d_bmats);
     p.wpack = reinterpret_cast<const uint8_t *>(s.d_wpack);
     p.B = (int)B; p.W = d.W; p.L = d.L;
     p.tiles_per_cta = s.tiles_per_cta; p.feats_per_cta = s.feats_per_cta; p.chunks_per_cta = s.chunks_per_cta;
@@ -561,47 +568,26 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
         for (int i = 0; i < kCMid * d.K2; ++i) sw += cw.w2[i];
         p.b2s = (float)((cw.b2 + sw) * (double)k2Log2e);
     }
-    dim3 grid((unsigned)((B + 2 * kTcM - 1) / (2 * kTcM)), s.n_ranges);
-    const size_t smem = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
-                        FuBars::kTotal * 8 + 16;
     const int arch_id = d.K1 == 10 ? 0 : 1;
-    if (s.opt_variant == 2 && d.C == 3 && s.splits == 3) {          // three window tiles per SM
-        dim3 grid3((unsigned)((B + kF3Tiles * kTcM - 1) / (kF3Tiles * kTcM)), s.n_ranges);
-        const size_t smem3 = (size_t)kF3Tiles * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
-                             F3Bars::kTotal * 8 + 16;
-        uint32_t stagger = 900;
-        if (const char *e = getenv("B2CNN_TC_STAGGER_NS")) stagger = (uint32_t)atoi(e);
-        cudaError_t e3;
-        if (arch_id == 0) {
-            e3 = cudaFuncSetAttribute(tc_fused3_kernel<3, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-            if (e3 == cudaSuccess) tc_fused3_kernel<3, 3, 0><<<grid3, kF3Threads, smem3, st>>>(tm, p, stagger);
-        } else {
-            e3 = cudaFuncSetAttribute(tc_fused3_kernel<3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-            if (e3 == cudaSuccess) tc_fused3_kernel<3, 3, 1><<<grid3, kF3Threads, smem3, st>>>(tm, p, stagger);
-        }
-        if (e3 != cudaSuccess) { *err = cudaGetErrorString(e3); return -1; }
-    } else
+    const int sp = s.splits;                          // bf16 pieces per conv1 weight: 3 (fp32-equivalent) or 2
+    p.bmats = reinterpret_cast<const uint8_t *>(sp == 2 ? s.d_bmats2 : s.d_bmats);
+    cudaError_t le = cudaSuccess;
+    bool launched = false;
     {
-    const size_t smem_ws = (size_t)4 * d.C * kTcABytes + (size_t)d.C * s.splits * kTcBBytes + 2 * kFuWChunkBytes +
-                           WsBars::kTotal * 8 + 16;
-#define WS_LAUNCH(CC, SS, AA)                                                                          \
-    if (s.opt_variant == 0 && d.C == CC && s.splits == SS && arch_id == AA) {                          \
-        cudaError_t e = cudaFuncSetAttribute(tc_fused_ws_kernel<CC, SS, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws); \
-        if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }                             \
-        tc_fused_ws_kernel<CC, SS, AA><<<grid, kWsThreads, smem_ws, st>>>(tm, p);                      \
-    } else
+        dim3 grid((unsigned)((B + 2 * kTcM - 1) / (2 * kTcM)), s.n_ranges);
+        const size_t smem = (size_t)4 * d.C * kTcABytes + (size_t)d.C * sp * kTcBBytes + 2 * kFuWChunkBytes + FuBars::kTotal * 8 + 16;
 #define FU_LAUNCH(CC, SS, AA)                                                                          \
-    if (d.C == CC && s.splits == SS && arch_id == AA) {                                                \
-        cudaError_t e = cudaFuncSetAttribute(tc_fused_kernel<CC, SS, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }                             \
-        tc_fused_kernel<CC, SS, AA><<<grid, kFuThreads, smem, st>>>(tm, p);                            \
-    } else
-    WS_LAUNCH(3, 3, 0) WS_LAUNCH(3, 3, 1)
-    FU_LAUNCH(3, 3, 0) FU_LAUNCH(3, 2, 0) FU_LAUNCH(2, 3, 0) FU_LAUNCH(1, 3, 0) FU_LAUNCH(3, 3, 1) FU_LAUNCH(2, 3, 1) FU_LAUNCH(1, 3, 1)
-    { *err = "no fused instantiation for this channel count / split"; return -1; }
+        if (!launched && d.C == CC && sp == SS && arch_id == AA) {                                     \
+            le = cudaFuncSetAttribute(tc_fused_kernel<CC, SS, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (le == cudaSuccess) tc_fused_kernel<CC, SS, AA><<<grid, kFuThreads, smem, st>>>(tm, p); \
+            launched = true;                                                                           \
+        }
+        FU_LAUNCH(3, 2, 0) FU_LAUNCH(3, 3, 0) FU_LAUNCH(2, 2, 0) FU_LAUNCH(1, 2, 0) FU_LAUNCH(2, 3, 0) FU_LAUNCH(1, 3, 0)
+        FU_LAUNCH(3, 2, 1) FU_LAUNCH(3, 3, 1) FU_LAUNCH(2, 2, 1) FU_LAUNCH(1, 2, 1) FU_LAUNCH(2, 3, 1) FU_LAUNCH(1, 3, 1)
 #undef FU_LAUNCH
-#undef WS_LAUNCH
     }
+    if (!launched) { *err = "no fused instantiation for this channel count / split"; return -1; }
+    if (le != cudaSuccess) { *err = cudaGetErrorString(le); return -1; }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     int launches = 1 + staged;

@@ -6,14 +6,14 @@ namespace b2cnn {
 
 struct TcState {
     bool ready = false;
-    int splits = 3;
-    void *d_bmats = nullptr;     // Toeplitz-expanded conv1 weights, bf16 pieces (see b2cnn_tc.cu)
+    int splits = 3;              // bf16 pieces per fp32 conv1 weight in the fused kernels (3 = fp32-equivalent)
+    void *d_bmats = nullptr;     // Toeplitz-expanded conv1 weights, three bf16 pieces (see b2cnn_tc.cu)
+    void *d_bmats2 = nullptr;    // the first two pieces only (tc_splits=2)
     void *d_wpack = nullptr;     // W_ih_l0 packed per (position range, 16-position chunk), 3 bf16 pieces
     int tiles_per_cta = 37, feats_per_cta = 514, chunks_per_cta = 33, n_ranges = 1;
     bool has_v1 = false;         // tc_frontend_kernel (features out) exists for this geometry (MyCNN5 only)
     bool fused_ready = false;    // fused conv + projection kernel usable (C <= 3)
     int64_t opt_fused = 1;
-    int64_t opt_variant = 1;     // 1 = tc_fused_kernel (2 window tiles/SM); 0 = warp-specialised epilogue; 2 = tc_fused3_kernel (3 tiles/SM)
 };
 
 const char *tc_error();

@@ -28,8 +28,17 @@
 
 namespace b2cnn {
 
+// B2CNN_ABLATE (experiments only, see scripts/build_ablations.sh): 1 = epilogue without math (tensor/TMA-side
+// ceiling), 2 = MUFU replaced by FMUL, 3 = conv1 MMAs not issued (epilogue-side ceiling).  Results are garbage.
+#ifndef B2CNN_ABLATE
+#define B2CNN_ABLATE 0
+#endif
 constexpr int kFuThreads = 384;
 constexpr int kFuWChunkBytes = 3 * 64 * 16 * 2;   // 3 pieces x (64 gates x 16 positions) bf16
+#ifndef B2CNN_COLLECTOR
+#define B2CNN_COLLECTOR 1
+#endif
+constexpr bool kFuCollector = B2CNN_COLLECTOR != 0;   // A-operand collector reuse across the piece-MMAs of a (block, channel)
 constexpr int kFuLag = 4;                         // conv1 blocks the MMA thread runs ahead before a projection chunk
 constexpr uint32_t kIdescProj = make_idesc_bf16(128, 64);
 
@@ -167,12 +176,20 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             if (elect_one()) {
                 const uint32_t d = tcol + slot * 32;
                 const uint32_t a_s = a_lo0 + (uint32_t)(s * C) * (kTcABytes >> 4) + n;
+#if B2CNN_ABLATE != 3
+                // the piece-MMAs of a (block, channel) share their A slice through the collector buffer
+                // (fill / use / lastuse) instead of re-reading 4 KB of shared memory per piece
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-#pragma unroll
-                    for (int sp = 0; sp < SPLITS; ++sp)
-                        umma_ss(d, a_s + c * (kTcABytes >> 4), a_hi, b_lo0 + (c * SPLITS + sp) * (kTcBBytes >> 4), b_hi, kIdesc,
-                                (c | sp) != 0);
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t a_c = a_s + c * (kTcABytes >> 4);
+                    const uint32_t b_c = b_lo0 + (c * SPLITS) * (kTcBBytes >> 4);
+                    umma_ss_coll<kFuCollector ? 1 : 0>(d, a_c, a_hi, b_c, b_hi, kIdesc, c != 0);
+                    if constexpr (SPLITS == 3) umma_ss_coll<kFuCollector ? 2 : 0>(d, a_c, a_hi, b_c + (kTcBBytes >> 4), b_hi, kIdesc, 1);
+                    umma_ss_coll<kFuCollector ? 3 : 0>(d, a_c, a_hi, b_c + (SPLITS - 1) * (kTcBBytes >> 4), b_hi, kIdesc, 1);
+                }
+#else
+                (void)d; (void)a_s;
+#endif
                 umma_commit(BAR(o + FuBars::kTFull + slot));
             }
             __syncwarp();
@@ -259,6 +276,22 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             }
             // ---------------- middle: straight-line math ----------------
             float2 an[4][2];
+#if B2CNN_ABLATE == 1
+            if constexpr (doA) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    an[r][0] = make_float2(__uint_as_float(Dbuf[PAR][r] ^ Dbuf[PAR][8 + r] ^ Dbuf[PAR][16 + r] ^ Dbuf[PAR][24 + r]), 0.f);
+                    an[r][1] = make_float2(__uint_as_float(Dbuf[PAR][4 + r] ^ Dbuf[PAR][12 + r] ^ Dbuf[PAR][20 + r] ^ Dbuf[PAR][28 + r]), 0.f);
+                }
+            }
+            if constexpr (doB) {
+                const uint32_t h = __float_as_uint(abuf[PAR][0][0].x) ^ __float_as_uint(abuf[PAR ^ 1][1][1].x);
+                const uint32_t acol = tlane + 128 + u * 24 + kk;
+                tmem_st1(acol, h & 0x3f803f80u);
+                tmem_st1(acol + 8, 0u);
+                tmem_st1(acol + 16, 0u);
+            }
+#else
             if constexpr (doA) {
                 auto Dv = [&](int idx) -> float { return __uint_as_float(Dbuf[PAR][idx]); };
                 if constexpr (ARCH == 0) {
@@ -336,6 +369,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 tmem_st1(acol + 8, md);
                 tmem_st1(acol + 16, lo);
             }
+#endif
             if constexpr (doA) {                            // a1(block jj) replaces a1(block jj-2)
 #pragma unroll
                 for (int q2 = 0; q2 < 2; ++q2)

@@ -168,6 +168,31 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t
         " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}"
         ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same MMA with an A-collector qualifier.  Consecutive MMAs of ONE issuing thread that multiply the same A
+// slice by different B matrices (the bf16 pieces of a band matrix) keep A in the tensor core's collector buffer
+// -- COLL 1 = ::fill (first), 2 = ::use, 3 = ::lastuse -- instead of re-reading 4 KB of shared memory each time
+// (SASS: UTCHMMA gdesc[..].A_KEEP / .A_REUSE.A_KEEP / .A_REUSE).  No other MMA may be issued in between.
+template <int COLL>
+__device__ __forceinline__ void umma_ss_coll(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    if constexpr (COLL == 1)
+        asm volatile(
+            "{\n .reg .pred p;\n .reg .b64 da, db;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n setp.ne.b32 p, %6, 0;\n"
+            " tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], da, db, %5, p;\n}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+    else if constexpr (COLL == 2)
+        asm volatile(
+            "{\n .reg .pred p;\n .reg .b64 da, db;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n setp.ne.b32 p, %6, 0;\n"
+            " tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], da, db, %5, p;\n}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+    else if constexpr (COLL == 3)
+        asm volatile(
+            "{\n .reg .pred p;\n .reg .b64 da, db;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n setp.ne.b32 p, %6, 0;\n"
+            " tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], da, db, %5, p;\n}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        umma_ss(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                         uint32_t accumulate) {
     asm volatile(
@@ -175,6 +200,13 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32
         " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n}"
         ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+#if defined(B2CNN_ABLATE) && B2CNN_ABLATE == 2
+#define B2CNN_EX2(dst, src) dst = (src) * 0.75f
+#define B2CNN_RCP(dst, src) dst = (src) * 0.75f
+#else
+#define B2CNN_EX2(dst, src) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(dst) : "f"(src))
+#define B2CNN_RCP(dst, src) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(dst) : "f"(src))
+#endif
 // ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two FMAs per issue slot ------------
 __device__ __forceinline__ uint64_t pk2(float2 v) {
     uint64_t r;
@@ -205,11 +237,11 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
 __device__ __forceinline__ float2 tanh_fold2(float2 m, float2 bias_scaled) {
     const float2 a = fma2(m, make_float2(k2Log2e, k2Log2e), bias_scaled);
     float e0, e1, r0, r1;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a.x));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a.y));
+    B2CNN_EX2(e0, a.x);
+    B2CNN_EX2(e1, a.y);
     const float2 d = add2(make_float2(e0, e1), make_float2(1.0f, 1.0f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+    B2CNN_RCP(r0, d.x);
+    B2CNN_RCP(r1, d.y);
     return fma2(make_float2(r0, r1), make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
 }
 // r = 1 / (1 + 2^(2 log2e (m + bias))) for two values: tanh(m + bias) == 1 - 2 r.  conv2 consumes r
@@ -238,17 +270,17 @@ __device__ __forceinline__ float2 sig_fold2(float2 m, float2 bias_scaled) {
     a.x = min_nan(a.x, 120.0f);
     a.y = min_nan(a.y, 120.0f);
 #endif
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a.x));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a.y));
+    B2CNN_EX2(e0, a.x);
+    B2CNN_EX2(e1, a.y);
     const float2 d = add2(make_float2(e0, e1), make_float2(1.0f, 1.0f));
 #if B2CNN_MONTGOMERY
     float rp;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rp) : "f"(d.x * d.y));
+    B2CNN_RCP(rp, d.x * d.y);
     return mul2(make_float2(rp, rp), make_float2(d.y, d.x));
 #else
     float r0, r1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+    B2CNN_RCP(r0, d.x);
+    B2CNN_RCP(r1, d.y);
     return make_float2(r0, r1);
 #endif
 }
