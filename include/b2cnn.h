@@ -121,6 +121,33 @@ int b2cnn_last_path(b2cnn_handle *h);
  * Synchronises on the stage's end event.  <0 if unavailable. */
 double b2cnn_last_stage_ms(b2cnn_handle *h, int stage);
 
+/* ---- The two steps in front of the model call, on the device (SURVEY.md section 8, rows f2 + f1) ----
+ * b2cnn_prep_windows replaces, for replay, what reaches bin/predictStream.py:105-139 through Kafka and
+ * Spark: the 180 s / 5 s sliding mean with nulls skipped (bin/processStream.py:196-208), forward-fill,
+ * back-fill and 0-fill of that grid (bin/processStream.py:62-123), and the 600 s / 60 s window assembly
+ * x_arr[0, signal_index, :] with zeros for absent signals (bin/predictStream.py:105-139,245-259).
+ *   raw        device pointer, int16 [n_samples][n_sig]: a WFDB format-16 numerics record as on disk
+ *              (-32768 = missing; physical = (adc - baseline) / gain, what wfdb.rdrecord returns,
+ *              bin/sendStream.py:46)
+ *   sel        host array [n_sel]: record columns of the model's signals; position i becomes model
+ *              channel i (the message index of bin/sendStream.py:59-64)
+ *   gains / baselines  host arrays [n_sig]
+ *   x_out      device pointer, [n_windows][n_channels][window_points] in `dtype` (f32 or bf16)
+ *   t0_out     device pointer or NULL, [n_windows] window start times in seconds
+ * The caller owns every buffer; the call allocates nothing and is asynchronous on `stream`. */
+typedef struct b2cnn_prep_config {
+    int32_t n_channels;    /* model input channels                 config.cfg CHANNEL_NAMES (10)      */
+    int32_t window_points; /* points per window                    config.cfg WINDOWSIZE (120)        */
+    int32_t grid_s;        /* slide of the smoothing window        processStream.py:199 (5 s)         */
+    int32_t smooth_s;      /* length of the smoothing window       processStream.py:199 (180 s)       */
+    int32_t stride_s;      /* slide of the model window            predictStream.py:252 (60 s)        */
+} b2cnn_prep_config;
+int64_t b2cnn_prep_window_count(int64_t n_samples, double fs, const b2cnn_prep_config *cfg);
+int64_t b2cnn_prep_workspace_bytes(int64_t n_samples, double fs, int32_t n_sel, const b2cnn_prep_config *cfg);
+int b2cnn_prep_windows(const int16_t *raw, int64_t n_samples, int32_t n_sig, const int32_t *sel, int32_t n_sel,
+                       const double *gains, const double *baselines, double fs, const b2cnn_prep_config *cfg,
+                       void *x_out, int dtype, double *t0_out, void *workspace, int64_t workspace_bytes, void *stream);
+
 const char *b2cnn_last_error(void);
 const char *b2cnn_version(void);
 

@@ -75,3 +75,96 @@ def test_replay_parity_gpu_vs_reference_scores():
     ref = O.RefMyCNN(O.ARCH_MYCNN5); ref.load_state_dict(sd); ref.eval()
     want = O.ref_independent_loop(ref, xt[:200], torch.full((200,), 65.0)).numpy()
     assert np.array_equal(want, g["logits"][:200]) and rel_err(logit[:200], want) <= 1e-4
+
+
+# ---- f2 + f1 on the device (csrc/b2cnn_prep.cu); the numpy restatement above is its oracle ----
+
+def _synthetic_record(seed, n, fs, n_sig=7, p_missing=0.2, lead_gap=0, dead=None):
+    rng = np.random.default_rng(seed)
+    names = ["HR", "PULSE", "junk A", "RESP", "SpO2", "NBPSys", "CVP"][:n_sig]
+    raw = rng.integers(-500, 3000, size=(n, n_sig)).astype(np.int16)
+    raw[rng.random((n, n_sig)) < p_missing] = -32768
+    if lead_gap:
+        raw[:lead_gap, 0] = -32768
+    if dead is not None:
+        raw[:, dead] = -32768
+    gains = rng.choice([1.0, 10.0, 12.5], size=n_sig)
+    bases = rng.integers(-5, 5, size=n_sig).astype(np.float64)
+    return S.NumericsRecord(tuple(names), gains, bases, fs, raw)
+
+
+def test_prep_window_count_matches_host_logic():
+    """Host-side arithmetic of the C ABI (no device work): window count of b2cnn_prep_window_count == numpy's."""
+    import ctypes
+    from tskd_b200 import capi
+    lib = capi.load_library()
+    cfg = capi.PrepConfig(S.N_CHANNELS, S.WINDOW_POINTS, S.GRID_S, S.SMOOTH_S, S.STRIDE_S)
+    for n, fs in [(1625, 1 / 60), (700, 1.0), (595, 1.0), (596, 1.0), (3000, 0.2), (12, 1 / 60), (2, 1.0)]:
+        t_last = (n - 1) * (1.0 / fs)
+        n_grid = int(np.floor(t_last / S.GRID_S)) + 1
+        want = len(np.arange(0, n_grid - S.WINDOW_POINTS + 1, S.STRIDE_S // S.GRID_S))
+        assert lib.b2cnn_prep_window_count(n, fs, ctypes.byref(cfg)) == want, (n, fs)
+    assert lib.b2cnn_prep_window_count(0, 1.0, ctypes.byref(cfg)) < 0
+    bad = capi.PrepConfig(10, 120, 5, 180, 62)                    # stride not a multiple of the grid
+    assert lib.b2cnn_prep_window_count(1000, 1.0, ctypes.byref(bad)) < 0
+
+
+@pytest.mark.gpu
+def test_gpu_window_assembly_matches_host_restatement_on_shipped_record():
+    g, _ = load_golden("p000194_replay.npz")
+    rec = _record(g)
+    want, t0w = S.assemble_windows(rec)
+    x, t0 = S.assemble_windows_gpu(rec, "cuda:0")
+    assert x.shape == (1615, 10, 120) and x.dtype == torch.float32
+    assert np.array_equal(t0.cpu().numpy(), t0w)
+    got = x.cpu().numpy()
+    w32 = want.astype(np.float32)                                  # predictStream.py:155 .float()
+    # the device sums every window directly, numpy takes prefix-sum differences (1e-12 cancellation residue where a
+    # window is all zeros); after the f32 cast (predictStream.py:155) nothing is off by more than an f32 ulp
+    assert np.abs(got.astype(np.float64) - want).max() <= 2e-7 * np.abs(want).max()
+    assert (np.abs(got - w32) <= 1e-9).mean() > 0.999
+    assert (got[:, 4:, :] == 0).all()
+    assert np.array_equal(got[0], g["x_first"].astype(np.float32))
+    xb, _ = S.assemble_windows_gpu(rec, "cuda:0", dtype=torch.bfloat16)
+    assert ((xb.float().cpu() - torch.from_numpy(w32)).abs() <= 2.0 ** -8 * torch.from_numpy(w32).abs() + 1e-30).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,fs,kw", [
+    (1, 1625, 1 / 60, {}), (2, 4000, 1.0, {"p_missing": 0.5}), (3, 900, 1.0, {"lead_gap": 400}),
+    (4, 2500, 0.2, {"dead": 1}), (5, 700, 1.0, {"p_missing": 0.0}), (6, 50000, 1.0, {"p_missing": 0.9}),
+    (7, 640, 1.0, {"n_sig": 2}),
+])
+def test_gpu_window_assembly_synthetic_records(seed, n, fs, kw):
+    rec = _synthetic_record(seed, n, fs, **kw)
+    want, t0w = S.assemble_windows(rec)
+    x, t0 = S.assemble_windows_gpu(rec, "cuda:0")
+    assert tuple(x.shape) == want.shape and np.array_equal(t0.cpu().numpy(), t0w)
+    got = x.cpu().numpy().astype(np.float64)
+    scale = max(1.0, float(np.abs(want).max()))
+    assert np.abs(got - want).max() <= 2e-7 * scale                # f32 rounding of the f64 grid values
+    assert (got[:, len(S.selected_signals(rec)):, :] == 0).all()   # absent signals are exact zeros (predictStream.py:131)
+
+
+@pytest.mark.gpu
+def test_replay_on_gpu_equals_host_assembled_replay():
+    g, _ = load_golden("p000194_replay.npz")
+    _, sd = load_golden("mycnn5_xtestinput.npz")
+    rec = _record(g)
+    model = tskd_b200.B200MyCNN.from_reference(sd).to("cuda:0")
+    rows_h = S.replay(model, rec, subject_id=194)
+    rows_d = S.replay(model, rec, subject_id=194, on_gpu=True)
+    assert len(rows_h) == len(rows_d) == 1615
+    assert [r[:2] for r in rows_h] == [r[:2] for r in rows_d]
+    assert rel_err(np.array([r[2] for r in rows_d]), g["probs"]) <= 1e-4
+    assert rel_err(np.array([r[2] for r in rows_d]), np.array([r[2] for r in rows_h])) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_prep_rejects_bad_arguments():
+    rec = _synthetic_record(9, 700, 1.0)
+    rec.gains[0] = 0.0
+    with pytest.raises(RuntimeError):
+        S.assemble_windows_gpu(rec, "cuda:0")
+    with pytest.raises(RuntimeError):
+        S.assemble_windows_gpu(_synthetic_record(9, 700, 1.0), "cpu")

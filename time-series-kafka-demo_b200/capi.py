@@ -23,7 +23,8 @@ FLAG_AFFINE = 1
 SYMBOLS = ("b2cnn_l_out", "b2cnn_weight_count", "b2cnn_create", "b2cnn_destroy",
            "b2cnn_set_weights", "b2cnn_workspace_bytes", "b2cnn_forward", "b2cnn_forward_host",
            "b2cnn_features", "b2cnn_set_option", "b2cnn_get_option", "b2cnn_last_launch_count",
-           "b2cnn_last_path", "b2cnn_last_stage_ms", "b2cnn_last_error", "b2cnn_version")
+           "b2cnn_last_path", "b2cnn_last_stage_ms", "b2cnn_last_error", "b2cnn_version",
+           "b2cnn_prep_window_count", "b2cnn_prep_workspace_bytes", "b2cnn_prep_windows")
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -35,6 +36,11 @@ class Config(ctypes.Structure):
                 ("in_channels", "k1", "c_mid", "k2", "pool_k", "pool_s", "hidden", "layers",
                  "window", "lstm_input", "act", "flags")] + \
                [("age_coef", ctypes.c_float), ("device", ctypes.c_int32)]
+
+
+class PrepConfig(ctypes.Structure):
+    """b2cnn_prep_config: the reference's window constants (config.cfg, processStream.py:199, predictStream.py:252)."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("n_channels", "window_points", "grid_s", "smooth_s", "stride_s")]
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -72,6 +78,13 @@ def load_library() -> ctypes.CDLL:
     lib.b2cnn_last_launch_count.argtypes = [c_vp]; lib.b2cnn_last_launch_count.restype = c_i64
     lib.b2cnn_last_path.argtypes = [c_vp]; lib.b2cnn_last_path.restype = c_int
     lib.b2cnn_last_stage_ms.argtypes = [c_vp, c_int]; lib.b2cnn_last_stage_ms.restype = ctypes.c_double
+    pcfg = ctypes.POINTER(PrepConfig)
+    lib.b2cnn_prep_window_count.argtypes = [c_i64, ctypes.c_double, pcfg]; lib.b2cnn_prep_window_count.restype = c_i64
+    lib.b2cnn_prep_workspace_bytes.argtypes = [c_i64, ctypes.c_double, ctypes.c_int32, pcfg]
+    lib.b2cnn_prep_workspace_bytes.restype = c_i64
+    lib.b2cnn_prep_windows.argtypes = [c_vp, c_i64, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.c_double, pcfg,
+                                       c_vp, c_int, c_vp, c_vp, c_i64, c_vp]
+    lib.b2cnn_prep_windows.restype = c_int
     lib.b2cnn_last_error.argtypes = []; lib.b2cnn_last_error.restype = ctypes.c_char_p
     lib.b2cnn_version.argtypes = []; lib.b2cnn_version.restype = ctypes.c_char_p
     _lib = lib

@@ -91,6 +91,26 @@ extern "C" int64_t b2cnn_weight_count(const b2cnn_config *cfg) {
 }
 
 extern "C" const char *b2cnn_last_error(void) { return g_err.c_str(); }
+
+// ---- preprocessing + window assembly (b2cnn_prep.cu) ----
+extern "C" int64_t b2cnn_prep_window_count(int64_t n_samples, double fs, const b2cnn_prep_config *cfg) {
+    const int64_t n = prep_window_count(n_samples, fs, cfg);
+    if (n < 0) fail(B2CNN_EINVAL, "b2cnn_prep_window_count: bad record shape / configuration");
+    return n;
+}
+extern "C" int64_t b2cnn_prep_workspace_bytes(int64_t n_samples, double fs, int32_t n_sel, const b2cnn_prep_config *cfg) {
+    const int64_t n = prep_workspace_bytes(n_samples, fs, n_sel, cfg);
+    if (n < 0) fail(B2CNN_EINVAL, "b2cnn_prep_workspace_bytes: bad record shape / configuration");
+    return n;
+}
+extern "C" int b2cnn_prep_windows(const int16_t *raw, int64_t n_samples, int32_t n_sig, const int32_t *sel, int32_t n_sel,
+                                  const double *gains, const double *baselines, double fs, const b2cnn_prep_config *cfg,
+                                  void *x_out, int dtype, double *t0_out, void *workspace, int64_t workspace_bytes, void *stream) {
+    const char *err = "";
+    const int rc = prep_windows(raw, n_samples, n_sig, sel, n_sel, gains, baselines, fs, cfg, x_out, dtype, t0_out, workspace,
+                                workspace_bytes, reinterpret_cast<cudaStream_t>(stream), &err);
+    return rc == B2CNN_OK ? rc : fail(rc, std::string("b2cnn_prep_windows: ") + err);
+}
 extern "C" const char *b2cnn_version(void) { return "b2cnn 0.1 (sm_100a; generic fp32 + tcgen05 conv1)"; }
 
 extern "C" int b2cnn_create(const b2cnn_config *cfg, b2cnn_handle **out) {

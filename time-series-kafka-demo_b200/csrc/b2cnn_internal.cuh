@@ -107,6 +107,13 @@ bool small_supported(const Dims &d);
 int launch_small_forward(const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int dtype, int64_t B,
                          const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
 
+// b2cnn_prep.cu: preprocessing + window assembly in front of the model call (f2 + f1)
+int64_t prep_window_count(int64_t n_samples, double fs, const b2cnn_prep_config *cfg);
+int64_t prep_workspace_bytes(int64_t n_samples, double fs, int n_sel, const b2cnn_prep_config *cfg);
+int prep_windows(const int16_t *raw, int64_t n_samples, int n_sig, const int *sel, int n_sel, const double *gains,
+                 const double *baselines, double fs, const b2cnn_prep_config *cfg, void *x_out, int dtype, double *t0_out,
+                 void *workspace, int64_t ws_bytes, cudaStream_t st, const char **err);
+
 void launch_transpose_wih(const float *wih0, float *wih0T, int L, cudaStream_t st);
 
 }  // namespace b2cnn

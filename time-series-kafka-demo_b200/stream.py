@@ -115,15 +115,66 @@ def assemble_windows(record: NumericsRecord) -> Tuple[np.ndarray, np.ndarray]:
     return x, starts * float(GRID_S)
 
 
+def assemble_windows_gpu(record: NumericsRecord, device="cuda", dtype=None):
+    """The same model inputs built ON THE DEVICE by libb2cnn's b2cnn_prep_windows (csrc/b2cnn_prep.cu): the raw
+    int16 record goes up once (a few KB), smoothing / filling / window assembly run as four small kernels and the
+    [n_windows, 10, 120] batch is written straight into the tensor predict() reads.  `assemble_windows` above is
+    the oracle of this path.  Returns (x [n_windows, 10, 120] f32|bf16 on `device`, t0 [n_windows] f64 seconds)."""
+    import ctypes
+
+    import torch
+
+    from . import capi
+    lib = capi.load_library()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("assemble_windows_gpu needs a CUDA device; there is no CPU fallback (use assemble_windows)")
+    dtype = dtype or torch.float32
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("dtype must be torch.float32 or torch.bfloat16")
+    sel = np.ascontiguousarray(selected_signals(record), dtype=np.int32)
+    gains = np.ascontiguousarray(record.gains, dtype=np.float64)
+    bases = np.ascontiguousarray(record.baselines, dtype=np.float64)
+    raw_h = np.ascontiguousarray(record.raw, dtype=np.int16)
+    n, n_sig = raw_h.shape
+    cfg = capi.PrepConfig(N_CHANNELS, WINDOW_POINTS, GRID_S, SMOOTH_S, STRIDE_S)
+    n_win = lib.b2cnn_prep_window_count(n, float(record.fs), ctypes.byref(cfg))
+    ws_bytes = lib.b2cnn_prep_workspace_bytes(n, float(record.fs), len(sel), ctypes.byref(cfg))
+    if n_win < 0 or ws_bytes < 0:
+        raise RuntimeError(f"b2cnn_prep: {capi.last_error()}")
+    with torch.cuda.device(dev):
+        raw_d = torch.from_numpy(raw_h).to(dev)
+        x = torch.empty((n_win, N_CHANNELS, WINDOW_POINTS), dtype=dtype, device=dev)
+        t0 = torch.empty((n_win,), dtype=torch.float64, device=dev)
+        ws = torch.empty((max(int(ws_bytes), 256),), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.b2cnn_prep_windows(raw_d.data_ptr(), n, n_sig, sel.ctypes.data, len(sel), gains.ctypes.data, bases.ctypes.data,
+                                    float(record.fs), ctypes.byref(cfg), x.data_ptr(), 0 if dtype == torch.float32 else 1,
+                                    t0.data_ptr(), ws.data_ptr(), int(ws.numel()), stream)
+        capi.check(rc, "b2cnn_prep_windows")
+        ws.record_stream(torch.cuda.current_stream(dev)); raw_d.record_stream(torch.cuda.current_stream(dev))
+    return x, t0
+
+
 def replay(model, record: NumericsRecord, subject_id: int, age: float = 65.0,
-           micro_batch: int = 0) -> List[Tuple[int, float, float]]:
+           micro_batch: int = 0, on_gpu: bool = False) -> List[Tuple[int, float, float]]:
     """Score every window of the record and return the rows the reference INSERTs into
     ``predictions`` (db/init.sql:24-28): (SUBJECT_ID, PRED_TIME [s since record start], RISK_SCORE).
     ``micro_batch`` = windows per predict() call (0 = all at once); NaN scores are dropped
-    like predictStream.py:171."""
+    like predictStream.py:171.  ``on_gpu`` builds the windows on the device (assemble_windows_gpu)."""
     import torch
-    x, t0 = assemble_windows(record)
     rows: List[Tuple[int, float, float]] = []
+    if on_gpu:                                                   # raw record -> windows -> scores without leaving the device
+        xg, t0g = assemble_windows_gpu(record, device=next(model.parameters()).device)
+        mb = micro_batch or max(len(xg), 1)
+        t0 = t0g.cpu().numpy()
+        for b0 in range(0, len(xg), mb):
+            prob = model.predict(xg[b0:b0 + mb], age, return_prob=True).cpu().numpy()
+            for tt, p in zip(t0[b0:b0 + mb], prob):
+                if not np.isnan(p):
+                    rows.append((int(subject_id), float(tt), float(p)))
+        return rows
+    x, t0 = assemble_windows(record)
     mb = micro_batch or len(x)
     for b0 in range(0, len(x), mb):
         xb = torch.from_numpy(x[b0:b0 + mb]).float()            # predictStream.py:155
