@@ -38,7 +38,8 @@ enum { B2CNN_DTYPE_F32 = 0, B2CNN_DTYPE_BF16 = 1 };
  *   (bin/models.py:29-30 with B>1; bin/utils.py:249). */
 enum { B2CNN_MODE_INDEPENDENT = 0, B2CNN_MODE_SEQUENCE = 1 };
 enum { B2CNN_ACT_TANH = 0, B2CNN_ACT_RELU = 1, B2CNN_ACT_IDENTITY = 2 };
-enum { B2CNN_PATH_AUTO = 0, B2CNN_PATH_GENERIC = 1, B2CNN_PATH_TENSORCORE = 2 };
+enum { B2CNN_PATH_AUTO = 0, B2CNN_PATH_GENERIC = 1, B2CNN_PATH_TENSORCORE = 2,
+       B2CNN_PATH_STREAM = 3 /* reported by b2cnn_last_path only: fp32 windows, streamed CUDA-core conv1 + tcgen05 projection */ };
 
 #define B2CNN_FLAG_AFFINE 1 /* per-channel scale/shift after each conv (folded eval-BatchNorm) */
 

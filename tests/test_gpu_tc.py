@@ -130,8 +130,11 @@ def test_tc_refuses_unsupported_shapes_instead_of_falling_back():
     with pytest.raises(RuntimeError, match="tensor"):
         m.predict(torch.zeros(4, 5, 2048, dtype=torch.bfloat16, device=DEV))
     _, m = _pair(3, 7504)
+    m.predict(torch.zeros(4, 3, 7504, dtype=torch.float32, device=DEV))       # fp32 input: the streaming kernel
+    assert m.last_path == "stream"
+    _, m = _pair(3, 7502)
     with pytest.raises(RuntimeError, match="tensor"):
-        m.predict(torch.zeros(4, 3, 7504, dtype=torch.float32, device=DEV))   # fp32 input
+        m.predict(torch.zeros(4, 3, 7502, dtype=torch.float32, device=DEV))   # fp32 rows that TMA cannot describe
 
 
 @pytest.mark.parametrize("C,W,B,dist", [(3, 7504, 300, "normal"), (3, 7504, 513, "physio"), (1, 2048, 130, "normal"),
@@ -159,3 +162,56 @@ def test_tc_fused_prefix_and_permutation_consistency():
     assert torch.equal(m.predict(x[:300], ages[:300]), y[:300])
     perm = torch.randperm(700, device=DEV)
     assert torch.equal(m.predict(x[perm], ages[perm]), y[perm])
+
+
+# ---- fp32 windows: streaming kernel (CUDA-core conv1 + tcgen05 projection), csrc/b2cnn_stream_f32.cuh ----
+
+@pytest.mark.parametrize("kind,C,W,B,dist", [
+    ("mycnn5", 3, 7504, 200, "normal"), ("mycnn5", 3, 7504, 300, "physio"), ("mycnn5", 1, 2048, 300, "normal"),
+    ("mycnn5", 2, 4000, 300, "normal"), ("mycnn3", 3, 7504, 257, "physio"), ("mycnn3", 2, 3000, 290, "normal"),
+    ("mycnn5", 3, 75000, 9, "normal"), ("mycnn5", 3, 7500, 33, "normal"), ("mycnn5", 3, 1528, 261, "normal"),
+])
+def test_f32_stream_kernel_matches_oracle_and_generic(kind, C, W, B, dist):
+    ref, m = _pair(C, W, path="auto", kind=kind)
+    _, mg = _pair(C, W, path="generic", kind=kind)
+    x = tskd_b200.synth.make_windows(B, C, W, dist, seed=61, dtype=torch.float32)
+    ages = tskd_b200.synth.make_ages(B, seed=61)
+    y = m.predict(x.to(DEV), ages.to(DEV))
+    assert m.last_path == "stream"
+    yg = mg.predict(x.to(DEV), ages.to(DEV))
+    assert mg.last_path == "generic"
+    want = O.ref_independent(ref, x, ages).numpy()
+    assert rel_err(y.cpu().numpy(), want) <= TOL
+    assert rel_err(y.cpu().numpy(), yg.cpu().numpy()) <= 2e-5
+    # batch-as-sequence semantics (reference model(x_batch)) share the front end
+    ys = m(x[:7].to(DEV), ages[:7].to(DEV))
+    assert rel_err(ys.cpu().numpy(), O.ref_sequence(ref, x[:7], ages[:7]).numpy()) <= TOL
+    # a window's logit does not depend on its batch (bit-for-bit while the same kernel serves the smaller batch;
+    # short windows in small batches take the single-launch kernel instead)
+    yh = m.predict(x[: B // 2].to(DEV), ages[: B // 2].to(DEV))
+    if m.last_path == "stream":
+        assert torch.equal(yh, y[: B // 2])
+    else:
+        assert rel_err(yh.cpu().numpy(), y[: B // 2].cpu().numpy()) <= 1e-6
+
+
+def test_f32_stream_kernel_nan_inf_pattern():
+    ref, m = _pair(3, 7504, path="auto")
+    x = tskd_b200.synth.make_windows(150, 3, 7504, "edge", seed=62, dtype=torch.float32)
+    x[3, 1, 100] = float("nan"); x[77, 0, 7503] = float("inf"); x[149, 2, 0] = float("-inf")
+    ages = torch.full((150,), 65.0)
+    want = O.ref_independent(ref, x, ages).numpy()
+    got = m.predict(x.to(DEV), ages.to(DEV)).cpu().numpy()
+    assert m.last_path == "stream"
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert rel_err(got[ok], want[ok]) <= TOL
+
+
+def test_f32_falls_back_to_generic_when_rows_are_not_16_byte_multiples():
+    ref, m = _pair(3, 7502, path="auto")           # W % 4 != 0: no TMA row pitch -> exact generic kernel
+    x = tskd_b200.synth.make_windows(20, 3, 7502, "normal", seed=63, dtype=torch.float32)
+    ages = tskd_b200.synth.make_ages(20, seed=63)
+    y = m.predict(x.to(DEV), ages.to(DEV))
+    assert m.last_path == "generic"
+    assert rel_err(y.cpu().numpy(), O.ref_independent(ref, x, ages).numpy()) <= TOL

@@ -40,6 +40,7 @@ struct b2cnn_handle {
     float *d_wih0T = nullptr;   // [L][64]
     int64_t n_weights = 0;
     int64_t opt_path = B2CNN_PATH_AUTO;
+    int64_t opt_stream = 1;      // fp32 windows: streaming kernel instead of the generic one
     int64_t opt_tc_splits = 3;   // bf16 pieces per conv1 weight in the fused kernels
     int64_t last_launches = 0;
     int last_path = 0;
@@ -250,7 +251,8 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
     const char *err = "";
     int launches = 0;
     const bool tc = use_tc(h, dtype, B, mode);
-    if (!tc && h->opt_path == B2CNN_PATH_TENSORCORE)
+    const bool stream = h->opt_path != B2CNN_PATH_GENERIC && h->opt_stream && tc_stream_supported(h->tc, d, dtype);
+    if (!tc && !stream && h->opt_path == B2CNN_PATH_TENSORCORE)
         return fail(B2CNN_EARCH, "path=tensorcore requested but this shape/dtype/mode is not supported by the tcgen05 kernel");
     const bool prof = h->opt_profile != 0;
     if (prof) {
@@ -271,6 +273,19 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
     // are windows, so it writes the transpose [L][B] (coalesced across lanes).
     int64_t sB = d.L, sP = 1;
     int n;
+    if (h->opt_path != B2CNN_PATH_GENERIC && h->opt_stream && tc_stream_supported(h->tc, d, dtype)) {
+        // fp32 windows: TMA-streamed CUDA-core conv1 + tcgen05 projection, features never leave the SM
+        n = tc_stream_gates(h->tc, d, h->cw, h->hw, x, B, feats, partial, gates, tc_ws, h->num_sms, st, &err);
+        if (n < 0) return fail(B2CNN_ECUDA, std::string("fp32 stream kernel: ") + err);
+        launches += n;
+        if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
+        n = launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
+        if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
+        launches += n;
+        if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }
+        h->last_launches = launches; h->last_path = B2CNN_PATH_STREAM;
+        return B2CNN_OK;
+    }
     if (tc && tc_fused_supported(h->tc, d, dtype)) {
         // conv + pool + projection fused on the tensor cores: the features never leave the SM
         n = tc_fused_gates(h->tc, d, h->cw, h->hw, x, B, feats, partial, gates, tc_ws, h->num_sms, st, &err);
@@ -421,6 +436,7 @@ extern "C" int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value)
     }
     if (!strcmp(key, "small_kernel")) { h->opt_small = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "tc_fused")) { h->tc.opt_fused = value ? 1 : 0; return B2CNN_OK; }
+    if (!strcmp(key, "stream_f32")) { h->opt_stream = value ? 1 : 0; return B2CNN_OK; }
     if (!strcmp(key, "profile")) { h->opt_profile = value ? 1 : 0; h->ev_valid = false; return B2CNN_OK; }
     if (!strcmp(key, "tc_splits")) {
         if (value != 2 && value != 3) return fail(B2CNN_EINVAL, "tc_splits must be 2 or 3");

@@ -264,6 +264,7 @@ __global__ void tc_compact_flags_kernel(int *flags, int B, int *list, int *count
 
 }  // namespace b2cnn
 #include "b2cnn_tc_fused.cuh"
+#include "b2cnn_stream_f32.cuh"
 namespace b2cnn {
 
 // ------------------------------------------------------------------------------------------
@@ -309,6 +310,7 @@ static bool arch_ok(const Dims &d) {
 }
 
 static int tiles_per_cta_for(const Dims &d);
+static int tiles_per_cta_s_for(const Dims &d);
 
 int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_wih0, const HeadWeights &, int splits, int,
                cudaStream_t st) {
@@ -363,6 +365,20 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
                                                                           s.feats_per_cta, s.chunks_per_cta, s.n_ranges, d.K1 == 10 ? 3 : 2);
         if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { g_tc_err = "pack W_ih"; return -1; }
         s.fused_ready = true;
+        // stream_f32_kernel: 3-block tiles, its own (L-only) position ranges
+        s.stream_ready = false;
+        s.tiles_per_cta_s = tiles_per_cta_s_for(d);
+        s.feats_per_cta_s = 2 * kSfBlocks * s.tiles_per_cta_s - 4;
+        s.chunks_per_cta_s = (kSfBlocks * s.tiles_per_cta_s + 7) / 8;
+        s.n_ranges_s = (d.L + s.feats_per_cta_s - 1) / s.feats_per_cta_s;
+        const size_t bytes_s = (size_t)s.n_ranges_s * s.chunks_per_cta_s * kFuWChunkBytes;
+        cudaFree(s.d_wpack_s); s.d_wpack_s = nullptr;
+        if (cudaMalloc(&s.d_wpack_s, bytes_s) != cudaSuccess) { g_tc_err = "cudaMalloc(packed W_ih, fp32 stream)"; return -1; }
+        const int64_t total_s = (int64_t)s.n_ranges_s * s.chunks_per_cta_s * 1024;
+        tc_pack_wih_kernel<<<(unsigned)((total_s + 255) / 256), 256, 0, st>>>(d_wih0, reinterpret_cast<uint8_t *>(s.d_wpack_s), d.L,
+                                                                            s.feats_per_cta_s, s.chunks_per_cta_s, s.n_ranges_s, d.K1 == 10 ? 3 : 2);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { g_tc_err = "pack W_ih (fp32 stream)"; return -1; }
+        s.stream_ready = true;
     }
     return 0;
 }
@@ -371,6 +387,9 @@ void tc_release(TcState &s) {
     cudaFree(s.d_bmats);
     cudaFree(s.d_bmats2);
     cudaFree(s.d_wpack);
+    cudaFree(s.d_wpack_s);
+    s.d_wpack_s = nullptr;
+    s.stream_ready = false;
     s.d_bmats = nullptr;
     s.d_bmats2 = nullptr;
     s.d_wpack = nullptr;
@@ -440,6 +459,15 @@ static int tiles_per_cta_for(const Dims &d) {
     int nt = ((d.L + 36) / 37 + 4 + 13) / 14;
     if (nt < 2) nt = 2;
     if (nt > 37) nt = 37;
+    return nt;
+}
+
+static int tiles_per_cta_s_for(const Dims &d) {
+    // stream_f32_kernel: about 37 position ranges (L only) like the bf16 kernel; a CTA's stream emits
+    // 6*tiles - 4 features (even: every range starts 16-byte aligned for TMA)
+    if (const char *e = getenv("B2CNN_SF_TILES")) { const int v = atoi(e); if (v >= 1 && v <= 16384) return v; }
+    int nt = ((d.L + 36) / 37 + 4 + 5) / 6;
+    if (nt < 4) nt = 4;
     return nt;
 }
 
@@ -523,7 +551,10 @@ int tc_features(TcState &s, const Dims &d, const ConvWeights &cw, const void *x,
 bool tc_fused_supported(const TcState &s, const Dims &d, int dtype) {
     return s.ready && s.fused_ready && s.opt_fused && dtype == B2CNN_DTYPE_BF16 && (arch_ok(d) || arch1_ok(d)) && d.C <= 3;
 }
-int tc_partial_slices(const TcState &s) { return s.fused_ready ? s.n_ranges : 0; }
+int tc_partial_slices(const TcState &s) {
+    if (!s.fused_ready) return 0;
+    return s.stream_ready && s.n_ranges_s > s.n_ranges ? s.n_ranges_s : s.n_ranges;
+}
 
 static int make_tmap(const Dims &d, const void *x, int64_t pitch, int64_t B, CUtensorMap *tm, const char **err) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
@@ -598,6 +629,79 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     launches += n;
     // the exception path: exact features + projection for flagged windows only
     n = launch_frontend_generic_listed(d, cw, x, B2CNN_DTYPE_BF16, B, feats, d.L, 1, list, count, st, num_sms, err);
+    if (n < 0) return -1;
+    launches += n;
+    proj_listed_kernel<<<64, 256, 0, st>>>(feats, d.L, 1, hw.wih0T, hw.bih0, hw.bhh0, gates, d.L, list, count);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    return launches + 1;
+}
+
+bool tc_stream_supported(const TcState &s, const Dims &d, int dtype) {
+    return s.ready && s.stream_ready && dtype == B2CNN_DTYPE_F32 && (arch_ok(d) || arch1_ok(d)) && d.C <= 3 && (d.W % 4) == 0;
+}
+
+// fp32 windows: streaming front end + projection -> gates[B][64]; flagged (NaN) windows are recomputed exactly.
+int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
+                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err) {
+    int *flags = reinterpret_cast<int *>(ws);
+    int *list = flags + B, *count = list + B;
+    if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
+    CUtensorMap tm;
+    {
+        cuuint64_t gdim[3] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)B};
+        cuuint64_t gstr[2] = {(cuuint64_t)d.W * 4, (cuuint64_t)d.C * d.W * 4};
+        cuuint32_t box[3] = {32, 1, kTcM};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(x), gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (fp32) failed"; return -1; }
+    }
+    StreamF32Params pp;
+    memset(&pp, 0, sizeof pp);
+    TcFusedParams &p = pp.f;
+    p.partial = partial; p.nanflag = flags;
+    p.wpack = reinterpret_cast<const uint8_t *>(s.d_wpack_s);
+    p.B = (int)B; p.W = d.W; p.L = d.L;
+    p.tiles_per_cta = s.tiles_per_cta_s; p.feats_per_cta = s.feats_per_cta_s; p.chunks_per_cta = s.chunks_per_cta_s;
+    for (int q2 = 0; q2 < 2; ++q2) {
+        for (int c = 0; c < d.C; ++c)
+            for (int k = 0; k < d.K1; ++k)
+                pp.w1p[c][k][q2] = make_float2(cw.w1[(c * d.K1 + k) * kCMid + 2 * q2], cw.w1[(c * d.K1 + k) * kCMid + 2 * q2 + 1]);
+        p.b1sp[q2] = make_float2(cw.b1[2 * q2] * k2Log2e, cw.b1[2 * q2 + 1] * k2Log2e);
+        for (int k = 0; k < 5; ++k) p.w2p[q2][k] = make_float2(-2.f * cw.w2[(2 * q2) * d.K2 + k], -2.f * cw.w2[(2 * q2 + 1) * d.K2 + k]);
+    }
+    {
+        double sw = 0.0;
+        for (int i = 0; i < kCMid * d.K2; ++i) sw += cw.w2[i];
+        p.b2s = (float)((cw.b2 + sw) * (double)k2Log2e);
+    }
+    dim3 grid((unsigned)((B + 2 * kTcM - 1) / (2 * kTcM)), s.n_ranges_s);
+    const size_t smem = (size_t)4 * d.C * kSfABytes + 2 * kFuWChunkBytes + SfBars::kTotal * 8 + 16;
+    const int arch_id = d.K1 == 10 ? 0 : 1;
+    cudaError_t le = cudaSuccess;
+    bool launched = false;
+#define SF_LAUNCH(CC, AA)                                                                              \
+    if (!launched && d.C == CC && arch_id == AA) {                                                     \
+        le = cudaFuncSetAttribute(stream_f32_kernel<CC, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (le == cudaSuccess) stream_f32_kernel<CC, AA><<<grid, kSfThreads, smem, st>>>(tm, pp);      \
+        launched = true;                                                                               \
+    }
+    SF_LAUNCH(3, 0) SF_LAUNCH(2, 0) SF_LAUNCH(1, 0) SF_LAUNCH(3, 1) SF_LAUNCH(2, 1) SF_LAUNCH(1, 1)
+#undef SF_LAUNCH
+    if (!launched) { *err = "no fp32 stream instantiation for this channel count"; return -1; }
+    if (le != cudaSuccess) { *err = cudaGetErrorString(le); return -1; }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    int launches = 1;
+    tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
+    ++launches;
+    int n = launch_reduce_gates(partial, s.n_ranges_s, B, hw, gates, st, err);
+    if (n < 0) return -1;
+    launches += n;
+    n = launch_frontend_generic_listed(d, cw, x, B2CNN_DTYPE_F32, B, feats, d.L, 1, list, count, st, num_sms, err);
     if (n < 0) return -1;
     launches += n;
     proj_listed_kernel<<<64, 256, 0, st>>>(feats, d.L, 1, hw.wih0T, hw.bih0, hw.bhh0, gates, d.L, list, count);

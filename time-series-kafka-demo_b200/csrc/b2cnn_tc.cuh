@@ -11,6 +11,9 @@ struct TcState {
     void *d_bmats2 = nullptr;    // the first two pieces only (tc_splits=2)
     void *d_wpack = nullptr;     // W_ih_l0 packed per (position range, 16-position chunk), 3 bf16 pieces
     int tiles_per_cta = 37, feats_per_cta = 514, chunks_per_cta = 33, n_ranges = 1;
+    void *d_wpack_s = nullptr;   // the same packing for the 3-block tiles of stream_f32_kernel (fp32 windows)
+    int tiles_per_cta_s = 86, feats_per_cta_s = 512, chunks_per_cta_s = 33, n_ranges_s = 1;
+    bool stream_ready = false;   // stream_f32_kernel usable (C <= 3)
     bool has_v1 = false;         // tc_frontend_kernel (features out) exists for this geometry (MyCNN5 only)
     bool fused_ready = false;    // fused conv + projection kernel usable (C <= 3)
     int64_t opt_fused = 1;
@@ -31,6 +34,10 @@ bool tc_fused_supported(const TcState &s, const Dims &d, int dtype);
 int tc_partial_slices(const TcState &s);
 int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err);
+// fp32 windows: streaming kernel with CUDA-core conv1 + tcgen05 projection (b2cnn_stream_f32.cuh)
+bool tc_stream_supported(const TcState &s, const Dims &d, int dtype);
+int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
+                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err);
 int tc_features(TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B, float *feats,
                 int num_sms, cudaStream_t st, const char **err);
 

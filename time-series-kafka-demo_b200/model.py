@@ -28,6 +28,7 @@ from .checkpoint import arch_of_module
 
 _PATHS = {"auto": capi.PATH_AUTO, "generic": capi.PATH_GENERIC, "tensorcore": capi.PATH_TENSORCORE}
 _PATH_NAMES = {v: k for k, v in _PATHS.items()}
+_PATH_NAMES[3] = "stream"            # B2CNN_PATH_STREAM: fp32 windows through the streaming kernel
 
 
 class B200MyCNN(nn.Module):
