@@ -215,6 +215,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-windows", type=int, default=48, help="windows per worker process and step (reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"],
+                    help="window dtype: bf16 is the BASELINE workload; f32 (the reference's native dtype) is an extra line")
     ap.add_argument("--tc-splits", type=int, default=3, help="bf16 pieces per fp32 conv1 weight on the tensor cores (3 = fp32-equivalent)")
     args = ap.parse_args()
 
@@ -244,7 +246,10 @@ def main():
     model = tskd_b200.B200MyCNN(arch, path=args.path, tc_splits=args.tc_splits).to(dev)
     if world > 1:
         broadcast_weights(model, src=0)                    # the one init-time NCCL collective
+    esz = 2 if args.dtype == "bf16" else 4
     x = tskd_b200.synth.make_windows(B, C, W, "normal", seed=1234 + rank, dtype=torch.bfloat16, device=dev)
+    if args.dtype == "f32":
+        x = x.float()                                      # same bf16-representable values, fp32 storage
     ages = tskd_b200.synth.make_ages(B, seed=1234 + rank, device=dev)
     model.set_profile(True)
 
@@ -307,9 +312,9 @@ def main():
         # algorithmic bytes per launch of the dominant kernel: every window's input
         # once (C*W*2 B) + its logit (4 B) + the weights once per launch
         n_w = sum(v.numel() for k, v in model.state_dict().items() if k in tskd_b200.arch.BLOB_KEYS)
-        alg_bytes = B * (C * W * 2 + 4) + n_w * 4
+        alg_bytes = B * (C * W * esz + 4) + n_w * 4
         achieved = alg_bytes / (k_ms / 1e3) / 1e9 if k_ms and k_ms > 0 else None
-        roof = {"bound": "hbm", "kernel": "front end (conv1+pool+conv2+pool)" if path == "generic" else "tcgen05 fused front end",
+        roof = {"bound": "hbm", "kernel": {"generic": "front end (conv1+pool+conv2+pool)", "stream": "fp32 streaming front end (CUDA-core conv1 + tcgen05 projection)"}.get(path, "tcgen05 fused front end"),
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None, "peak_source": peak_src,
                 "kernel_ms": k_ms, "head_ms": head_ms, "algorithmic_bytes_per_launch": alg_bytes,
@@ -318,10 +323,10 @@ def main():
                 "compute_note": "co-bound by FP32/MUFU: 21.9 MFLOP + 169k tanh per window (DESIGN.md)"}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "bf16 in / f32 math", "data": "synthetic",
-               "config": dict(workload(B), path=path, parallelism=f"dp{world} (window shards, no data-path collective)"),
+               "scaling": "weak", "vs_baseline": None, "dtype": "bf16 in / f32 math" if args.dtype == "bf16" else "f32", "data": "synthetic",
+               "config": dict(workload(B) if args.dtype == "bf16" else dict(workload(B), workload=workload(B)["workload"].replace("bf16", "fp32 (extra line, not the BASELINE dtype)")), path=path, parallelism=f"dp{world} (window shards, no data-path collective)"),
                "roofline": roof, "clocks": clocks,
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (C * W * 2 + 4),
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (C * W * esz + 4),
                        "d2h_bytes_per_step": B * 4, "steps": args.e2e_steps, "note": "per GPU; pinned host tensors through predict()"},
                "gpu_launches": launches_per_step * args.steps}
         if world == 1 and not args.no_cpu_baseline:

@@ -275,11 +275,15 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
     int n;
     if (h->opt_path != B2CNN_PATH_GENERIC && h->opt_stream && tc_stream_supported(h->tc, d, dtype)) {
         // fp32 windows: TMA-streamed CUDA-core conv1 + tcgen05 projection, features never leave the SM
-        n = tc_stream_gates(h->tc, d, h->cw, h->hw, x, B, feats, partial, gates, tc_ws, h->num_sms, st, &err);
+        const bool indep = mode == B2CNN_MODE_INDEPENDENT;
+        int slices = 0;
+        n = tc_stream_gates(h->tc, d, h->cw, h->hw, x, B, feats, partial, gates, tc_ws, h->num_sms, st, &err, !indep, &slices);
         if (n < 0) return fail(B2CNN_ECUDA, std::string("fp32 stream kernel: ") + err);
         launches += n;
         if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
-        n = launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
+        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, reinterpret_cast<const int *>(tc_ws), gates, B, age, n_age,
+                                            apply_sigmoid, out, st, &err)
+                  : launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
         if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
         launches += n;
         if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }
@@ -288,11 +292,15 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
     }
     if (tc && tc_fused_supported(h->tc, d, dtype)) {
         // conv + pool + projection fused on the tensor cores: the features never leave the SM
-        n = tc_fused_gates(h->tc, d, h->cw, h->hw, x, B, feats, partial, gates, tc_ws, h->num_sms, st, &err);
+        const bool indep = mode == B2CNN_MODE_INDEPENDENT;
+        int slices = 0;
+        n = tc_fused_gates(h->tc, d, h->cw, h->hw, x, B, feats, partial, gates, tc_ws, h->num_sms, st, &err, !indep, &slices);
         if (n < 0) return fail(B2CNN_ECUDA, std::string("tensor-core fused kernel: ") + err);
         launches += n;
         if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
-        n = launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
+        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, reinterpret_cast<const int *>(tc_ws), gates, B, age, n_age,
+                                            apply_sigmoid, out, st, &err)
+                  : launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
         if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
         launches += n;
         if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }

@@ -158,6 +158,79 @@ head_independent_kernel(const float *__restrict__ gates0, HeadWeights hw, const 
     out[b] = apply_sigmoid ? sigmoid_acc(y) : y;
 }
 
+// Independent windows, reduction fused in: 16 lanes per window (lane u = hidden unit u), 16 windows per CTA.
+// gates0[b][g] = (sum_k partial[k][b][g] + b_ih[g]) + b_hh[g] in the same fixed order as reduce_gates_kernel,
+// unless the window was flagged by a tensor-core front end, in which case its exactly recomputed row of
+// `gates_listed` is taken.  The arithmetic per window is that of head_independent_kernel, term for term.
+__global__ void __launch_bounds__(256)
+head_reduce_independent_kernel(const float *__restrict__ part, int slices, const int *__restrict__ flags,
+                               const float *__restrict__ gates_listed, HeadWeights hw, const float *__restrict__ age,
+                               int64_t n_age, float coef, int apply_sigmoid, float *__restrict__ out, int64_t B) {
+    __shared__ float s_w1[kHidden][kGates];                // W_ih_l1 transposed: s_w1[k][row], conflict-free per k
+    for (int i = threadIdx.x; i < kGates * kHidden; i += blockDim.x) s_w1[i & 15][i >> 4] = __ldg(hw.wih1 + i);
+    const int lane = threadIdx.x & 31, u = lane & 15;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = b < B;
+    const int64_t bb = live ? b : B - 1;                   // dead lanes shadow the last window (shuffles stay full-warp)
+    float g4[4];
+    if (flags && flags[bb]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g4[q] = gates_listed[bb * kGates + q * kHidden + u];
+    } else {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        int k = 0;
+        for (; k + 8 <= slices; k += 8) {                  // 32 loads in flight per lane; sums stay in slice order
+            float v[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float *pk = part + ((int64_t)(k + j) * B + bb) * kGates + u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[j][q] = __ldg(pk + q * kHidden);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s4[q] += v[j][q];
+        }
+        for (; k < slices; ++k) {
+            const float *pk = part + ((int64_t)k * B + bb) * kGates + u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s4[q] += __ldg(pk + q * kHidden);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g4[q] = (s4[q] + __ldg(hw.bih0 + q * kHidden + u)) + __ldg(hw.bhh0 + q * kHidden + u);
+    }
+    __syncthreads();                                       // s_w1 complete
+    // layer 0 from the zero state
+    const float c0 = sigmoid_acc(g4[1]) * 0.f + sigmoid_acc(g4[0]) * tanhf(g4[2]);
+    const float h0 = sigmoid_acc(g4[3]) * tanhf(c0);
+    // layer 1: gi[q] = (sum_k W_ih_l1[q*16+u][k] h0[k] + b_ih) + b_hh, k ascending
+    float gi[4] = {0.f, 0.f, 0.f, 0.f};
+    const int base = lane & 16;
+#pragma unroll
+    for (int k = 0; k < kHidden; ++k) {
+        const float hk = __shfl_sync(0xffffffffu, h0, base + k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gi[q] = fmaf(s_w1[k][q * kHidden + u], hk, gi[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gi[q] = (gi[q] + __ldg(hw.bih1 + q * kHidden + u)) + __ldg(hw.bhh1 + q * kHidden + u);
+    const float c1 = sigmoid_acc(gi[1]) * 0.f + sigmoid_acc(gi[0]) * tanhf(gi[2]);
+    const float h1 = sigmoid_acc(gi[3]) * tanhf(c1);
+    // Linear(16 -> 1): y = fma(wo[u], h1[u], y) for u ascending, exactly as the one-thread-per-window kernel
+    float y = 0.f;
+#pragma unroll
+    for (int k = 0; k < kHidden; ++k) {
+        const float hk = __shfl_sync(0xffffffffu, h1, base + k);
+        y = fmaf(__ldg(hw.wo + k), hk, y);
+    }
+    if (live && u == 0) {
+        y += __ldg(hw.bo);
+        y *= age_scale(age[n_age == 1 ? 0 : b], coef);
+        out[b] = apply_sigmoid ? sigmoid_acc(y) : y;
+    }
+}
+
 // One warp scans the B rows sequentially.  Lane l owns gate rows l and l+32 of every weight
 // matrix (registers); units' (h, c) are held twice, by lanes u and u+16.
 __global__ void __launch_bounds__(32)
@@ -254,6 +327,17 @@ int launch_reduce_gates(const float *partial, int slices, int64_t B, const HeadW
                         cudaStream_t st, const char **err) {
     const int64_t n = B * kGates;
     reduce_gates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, slices, B, hw.bih0, hw.bhh0, gates);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    return 1;
+}
+
+// independent windows: slice reduction + LSTM cells + Linear + age scale in one launch
+int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, const int *flags,
+                            const float *gates_listed, int64_t B, const float *age, int64_t n_age, int apply_sigmoid,
+                            float *out, cudaStream_t st, const char **err) {
+    head_reduce_independent_kernel<<<(unsigned)((B * 16 + 255) / 256), 256, 0, st>>>(partial, slices, flags, gates_listed, hw, age,
+                                                                                  n_age, d.age_coef, apply_sigmoid, out, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     return 1;

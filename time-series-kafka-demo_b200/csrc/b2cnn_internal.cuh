@@ -100,6 +100,10 @@ int launch_reduce_gates(const float *partial, int slices, int64_t B, const HeadW
 int launch_lstm_head(const Dims &d, const HeadWeights &hw, const float *gates, int64_t B, const float *age,
                      int64_t n_age, int mode, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
 
+int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, const int *flags,
+                            const float *gates_listed, int64_t B, const float *age, int64_t n_age, int apply_sigmoid,
+                            float *out, cudaStream_t st, const char **err);
+
 int choose_ksplit(int64_t B, int L, int num_sms);
 
 // b2cnn_small.cu: whole forward pass of short windows in one launch (independent windows only)

@@ -194,7 +194,7 @@ stream_f32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
                 for (int sft = 0; sft < 8; ++sft) { D[sft][0] = make_float2(0.f, 0.f); D[sft][1] = make_float2(0.f, 0.f); }
                 const uint8_t *tile = sA_of(t, s, 0) + row * 128;
-#pragma unroll
+#pragma unroll 1
                 for (int c = 0; c < C; ++c) {
                     float xs[16];
 #pragma unroll

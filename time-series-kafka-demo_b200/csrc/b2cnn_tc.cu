@@ -256,10 +256,7 @@ tc_frontend_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 // windows flagged by the tensor-core kernel -> compact index list for the exact re-computation
 __global__ void tc_compact_flags_kernel(int *flags, int B, int *list, int *count) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B && flags[b]) {
-        flags[b] = 0;
-        list[atomicAdd(count, 1)] = b;
-    }
+    if (b < B && flags[b]) list[atomicAdd(count, 1)] = b;      // flags stay set: the head kernel picks the recomputed rows by them
 }
 
 }  // namespace b2cnn
@@ -571,7 +568,8 @@ static int make_tmap(const Dims &d, const void *x, int64_t pitch, int64_t B, CUt
 
 // fused front end + projection -> gates[B][64]; flagged (NaN) windows are recomputed exactly.
 int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
-                   float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err) {
+                   float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err,
+                   bool reduce_here, int *slices_out) {
     int *flags = reinterpret_cast<int *>(ws);
     int *list = flags + B, *count = list + B;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) { *err = "memset flags"; return -1; }
@@ -624,7 +622,10 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     int launches = 1 + staged;
     tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
     ++launches;
-    int n = launch_reduce_gates(partial, s.n_ranges, B, hw, gates, st, err);
+    // reduce_here == false: the caller's head kernel sums the range partials itself (independent windows) and only
+    // takes gates[b] for flagged windows, which the two launches below recompute exactly
+    if (slices_out) *slices_out = s.n_ranges;
+    int n = reduce_here ? launch_reduce_gates(partial, s.n_ranges, B, hw, gates, st, err) : 0;
     if (n < 0) return -1;
     launches += n;
     // the exception path: exact features + projection for flagged windows only
@@ -643,7 +644,8 @@ bool tc_stream_supported(const TcState &s, const Dims &d, int dtype) {
 
 // fp32 windows: streaming front end + projection -> gates[B][64]; flagged (NaN) windows are recomputed exactly.
 int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
-                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err) {
+                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err,
+                    bool reduce_here, int *slices_out) {
     int *flags = reinterpret_cast<int *>(ws);
     int *list = flags + B, *count = list + B;
     if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) { *err = "memset flags"; return -1; }
@@ -698,7 +700,8 @@ int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const Head
     int launches = 1;
     tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
     ++launches;
-    int n = launch_reduce_gates(partial, s.n_ranges_s, B, hw, gates, st, err);
+    if (slices_out) *slices_out = s.n_ranges_s;
+    int n = reduce_here ? launch_reduce_gates(partial, s.n_ranges_s, B, hw, gates, st, err) : 0;
     if (n < 0) return -1;
     launches += n;
     n = launch_frontend_generic_listed(d, cw, x, B2CNN_DTYPE_F32, B, feats, d.L, 1, list, count, st, num_sms, err);

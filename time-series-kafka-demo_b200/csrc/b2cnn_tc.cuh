@@ -33,11 +33,13 @@ int tc_frontend(TcState &s, const Dims &d, const ConvWeights &cw, const void *x,
 bool tc_fused_supported(const TcState &s, const Dims &d, int dtype);
 int tc_partial_slices(const TcState &s);
 int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
-                   float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err);
+                   float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err,
+                   bool reduce_here = true, int *slices_out = nullptr);
 // fp32 windows: streaming kernel with CUDA-core conv1 + tcgen05 projection (b2cnn_stream_f32.cuh)
 bool tc_stream_supported(const TcState &s, const Dims &d, int dtype);
 int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
-                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err);
+                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err,
+                    bool reduce_here = true, int *slices_out = nullptr);
 int tc_features(TcState &s, const Dims &d, const ConvWeights &cw, const void *x, int64_t B, float *feats,
                 int num_sms, cudaStream_t st, const char **err);
 
