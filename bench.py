@@ -343,7 +343,8 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # committed ncu captures under profiles/ (None until a capture exists for that path).
 TRAFFIC = {"generic": 1.846642e9 + 0.297926e9,      # profiles/r01_generic_frontend_ncu_full.txt (features written to HBM)
-           "tensorcore": 1.944909e9 + 0.033627e9}   # profiles/r01_final_fused_ncu_full.txt (halo re-reads + gate partials)
+           "tensorcore": 1.944850e9 + 0.034090e9,   # profiles/r01_final_fused_ncu_full.txt (halo re-reads + gate partials)
+           "stream": 3.801502e9 + 0.034493e9}       # profiles/r01_final_stream_ncu_full.txt (fp32 windows)
 
 if __name__ == "__main__":
     main()
