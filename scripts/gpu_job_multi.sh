@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/m_build.log 2>&1
 nvidia-smi -L > gpurun_out/m_smi.txt
-for n in 1 $N; do
+for n in ${NS:-1 $N}; do
   if [ $n -eq 1 ]; then
     timeout -k 10 400 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/m_bench_n1.json 2> gpurun_out/m_bench_n1.err
   else
