@@ -1,18 +1,23 @@
 #!/bin/bash
-# milestone job: full GPU test suite, smoke, bench (both arms), ncu launch list + full capture
+# milestone job 2: full tests, smoke, both bench arms, sweep, profiles
 set -x
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.build()" > gpurun_out/f_build.log 2>&1
-timeout -k 10 900 python -m pytest tests -m gpu -q > gpurun_out/f_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/f_pytest.log
-tail -6 gpurun_out/f_pytest.log
-timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/f_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/f_smoke.log
-cat gpurun_out/f_smoke.log
-timeout -k 10 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/f_bench_ref.json 2> gpurun_out/f_bench.err
-cat gpurun_out/f_bench_ref.json
-timeout -k 10 600 python bench.py --steps 20 --warmup 3 > gpurun_out/f_bench.json 2>> gpurun_out/f_bench.err; echo "bench rc=$?"
-cat gpurun_out/f_bench.json; tail -5 gpurun_out/f_bench.err
-timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/f_launches.csv \
-    python bench.py --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/f_ncu_launch.log 2>&1
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:tc_fused -s 2 -c 1 -o gpurun_out/f_fused \
-    python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/f_ncu_full.log 2>&1
-ls -la gpurun_out | head -40
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/g_build.log 2>&1
+timeout -k 10 900 python -m pytest tests -m gpu -q > gpurun_out/g_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/g_pytest.log
+tail -6 gpurun_out/g_pytest.log
+timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/g_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/g_smoke.log
+cat gpurun_out/g_smoke.log
+timeout -k 10 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/g_bench_ref.json 2> gpurun_out/g_bench.err
+cut -c1-300 gpurun_out/g_bench_ref.json; grep -o '"cpu_baseline".*' gpurun_out/g_bench_ref.json | cut -c1-500
+timeout -k 10 600 python bench.py --steps 20 --warmup 3 > gpurun_out/g_bench.json 2>> gpurun_out/g_bench.err; echo "bench rc=$?"
+cat gpurun_out/g_bench.json; tail -5 gpurun_out/g_bench.err
+timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --dtype f32 > gpurun_out/g_bench_f32.json 2>> gpurun_out/g_bench.err; echo "bench f32 rc=$?"
+cut -c1-200 gpurun_out/g_bench_f32.json
+timeout -k 10 900 python scripts/sweep.py > gpurun_out/g_sweep.jsonl 2> gpurun_out/g_sweep.err; echo "sweep rc=$?"; cat gpurun_out/g_sweep.jsonl | cut -c1-330; tail -3 gpurun_out/g_sweep.err
+timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/g_launches.csv \
+    python bench.py --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/g_ncu_launch.log 2>&1
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:tc_fused -s 2 -c 1 -o gpurun_out/g_fused \
+    python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/g_ncu_full.log 2>&1
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:stream_f32 -s 2 -c 1 -o gpurun_out/g_stream \
+    python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline --dtype f32 > gpurun_out/g_ncu_full_f32.log 2>&1
+ls gpurun_out | grep "^g_"
