@@ -241,9 +241,10 @@ stream_f32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 }
             }
             if constexpr (doB) {
-                float2 acc[4][2];
+                // one accumulator per output position over both channel pairs: c2 = acc.x + acc.y (no pair-sum step)
+                float2 acc[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
+                for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int q2 = 0; q2 < 2; ++q2) {
                     const float2 A8[8] = {abuf[PAR][0][q2], abuf[PAR][1][q2], abuf[PAR][2][q2], abuf[PAR][3][q2],
@@ -251,14 +252,11 @@ stream_f32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < 5; ++k)
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) acc[r][q2] = fma2(p.w2p[q2][k], A8[r + k], acc[r][q2]);
+                        for (int r = 0; r < 4; ++r) acc[r] = fma2(p.w2p[q2][k], A8[r + k], acc[r]);
                 }
                 float c2[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float2 sacc = add2(acc[r][0], acc[r][1]);
-                    c2[r] = sacc.x + sacc.y;
-                }
+                for (int r = 0; r < 4; ++r) c2[r] = acc[r].x + acc[r].y;
                 float2 f;
                 if constexpr (ARCH == 0) {
                     f = tanh_fold2(make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3])), make_float2(p.b2s, p.b2s));

@@ -331,9 +331,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             }
             if constexpr (doB) {
                 // conv2 on r = (1 - tanh)/2 (weights pre-multiplied by -2, bias absorbs sum(w)): 40 FFMA2
-                float2 acc[4][2];
+                // one accumulator per output position over both channel pairs: c2 = acc.x + acc.y (no pair-sum step)
+                float2 acc[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
+                for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int q2 = 0; q2 < 2; ++q2) {
                     // a1(step jb-1) = abuf[PAR], a1(step jb) = abuf[PAR ^ 1]
@@ -342,14 +343,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < 5; ++k)
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) acc[r][q2] = fma2(w2r[q2][k], A8[r + k], acc[r][q2]);
+                        for (int r = 0; r < 4; ++r) acc[r] = fma2(w2r[q2][k], A8[r + k], acc[r]);
                 }
                 float c2[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float2 sacc = add2(acc[r][0], acc[r][1]);
-                    c2[r] = sacc.x + sacc.y;
-                }
+                for (int r = 0; r < 4; ++r) c2[r] = acc[r].x + acc[r].y;
                 float2 f;                                                    // features 2*jb-FOFF, 2*jb-FOFF+1
                 if constexpr (ARCH == 0) {
                     f = tanh_fold2(make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3])), make_float2(p.b2s, p.b2s));
