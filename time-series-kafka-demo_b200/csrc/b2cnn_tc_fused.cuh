@@ -39,7 +39,10 @@ constexpr int kFuWChunkBytes = 3 * 64 * 16 * 2;   // 3 pieces x (64 gates x 16 p
 #define B2CNN_COLLECTOR 1
 #endif
 constexpr bool kFuCollector = B2CNN_COLLECTOR != 0;   // A-operand collector reuse across the piece-MMAs of a (block, channel)
-constexpr int kFuLag = 4;                         // conv1 blocks the MMA thread runs ahead before a projection chunk
+#ifndef B2CNN_FULAG
+#define B2CNN_FULAG 4                             // A/B-timed: 2 -> +4 %, 6 -> +0.4 % kernel time
+#endif
+constexpr int kFuLag = B2CNN_FULAG;                         // conv1 blocks the MMA thread runs ahead before a projection chunk
 constexpr uint32_t kIdescProj = make_idesc_bf16(128, 64);
 
 struct TcFusedParams {

@@ -266,7 +266,7 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
 __device__ __forceinline__ float2 sig_fold2(float2 m, float2 bias_scaled) {
     float2 a = fma2(m, make_float2(k2Log2e, k2Log2e), bias_scaled);
     float e0, e1;
-#if B2CNN_MONTGOMERY
+#if B2CNN_MONTGOMERY && !defined(B2CNN_EXP_NOCLAMP)           // NOCLAMP: timing experiment only (0 * inf -> NaN for |x| > 44)
     a.x = min_nan(a.x, 120.0f);
     a.y = min_nan(a.y, 120.0f);
 #endif
