@@ -13,6 +13,8 @@ timeout -k 10 600 python bench.py --steps 20 --warmup 3 > gpurun_out/g_bench.jso
 cat gpurun_out/g_bench.json; tail -5 gpurun_out/g_bench.err
 timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --dtype f32 > gpurun_out/g_bench_f32.json 2>> gpurun_out/g_bench.err; echo "bench f32 rc=$?"
 cut -c1-200 gpurun_out/g_bench_f32.json
+timeout -k 10 300 python bench.py --batch 32768 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/g_bench_b32768.json 2>> gpurun_out/g_bench.err; echo "bench B=32768 rc=$?"
+cut -c1-200 gpurun_out/g_bench_b32768.json
 timeout -k 10 900 python scripts/sweep.py > gpurun_out/g_sweep.jsonl 2> gpurun_out/g_sweep.err; echo "sweep rc=$?"; cat gpurun_out/g_sweep.jsonl | cut -c1-330; tail -3 gpurun_out/g_sweep.err
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/g_launches.csv \
     python bench.py --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/g_ncu_launch.log 2>&1
