@@ -108,12 +108,14 @@ int b2cnn_features(b2cnn_handle *h, const void *x, int dtype, int64_t B, float *
 
 /* Options: "path" = B2CNN_PATH_*; "tc_splits" = 2|3: bf16 pieces per fp32 conv1 weight on the
  * tensor cores (3, default: exact fp32 weights; 2: weights rounded to 16 mantissa bits);
+ * "stream_f32" = 0|1 (default 1): fp32 windows take the streaming kernel instead of the generic one;
+ * "tc_fused" = 0|1 (default 1): bf16 windows take the fused conv+projection kernel; "small_kernel" = 0|1;
  * "profile" = 0|1: record CUDA events around the stages of each b2cnn_forward on its stream. */
 int b2cnn_set_option(b2cnn_handle *h, const char *key, int64_t value);
 int64_t b2cnn_get_option(b2cnn_handle *h, const char *key);
 
 /* Kernel launches issued by the most recent forward on this handle (bench: gpu_launches),
- * and which path it took (B2CNN_PATH_GENERIC / B2CNN_PATH_TENSORCORE). */
+ * and which path it took (B2CNN_PATH_GENERIC / B2CNN_PATH_TENSORCORE / B2CNN_PATH_STREAM). */
 int64_t b2cnn_last_launch_count(b2cnn_handle *h);
 int b2cnn_last_path(b2cnn_handle *h);
 

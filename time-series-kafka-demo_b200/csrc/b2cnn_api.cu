@@ -112,7 +112,7 @@ extern "C" int b2cnn_prep_windows(const int16_t *raw, int64_t n_samples, int32_t
                                 workspace_bytes, reinterpret_cast<cudaStream_t>(stream), &err);
     return rc == B2CNN_OK ? rc : fail(rc, std::string("b2cnn_prep_windows: ") + err);
 }
-extern "C" const char *b2cnn_version(void) { return "b2cnn 0.1 (sm_100a; generic fp32 + tcgen05 conv1)"; }
+extern "C" const char *b2cnn_version(void) { return "b2cnn 0.2 (sm_100a; tcgen05 fused bf16 path, fp32 streaming path, generic path, device preprocessing)"; }
 
 extern "C" int b2cnn_create(const b2cnn_config *cfg, b2cnn_handle **out) {
     if (!cfg || !out) return fail(B2CNN_EINVAL, "b2cnn_create: null argument");
