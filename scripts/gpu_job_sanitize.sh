@@ -29,5 +29,7 @@ rec = S.NumericsRecord(tuple(str(n) for n in gd["names"]), gd["gains"], gd["base
 xg, t0 = S.assemble_windows_gpu(rec, "cuda:0"); torch.cuda.synchronize()
 print("prep", tuple(xg.shape))
 PY
-timeout -k 10 1200 compute-sanitizer --tool memcheck --print-limit 20 python /tmp/san.py > gpurun_out/san_memcheck.log 2>&1; echo "memcheck rc=$?"
-grep -c "Invalid\|out of bounds\|misaligned" gpurun_out/san_memcheck.log; tail -12 gpurun_out/san_memcheck.log
+for tool in ${TOOLS:-memcheck racecheck synccheck}; do
+timeout -k 10 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/san_$tool.log 2>&1; echo "$tool rc=$?"
+grep -c "Invalid\|out of bounds\|misaligned\|hazard\|Barrier error" gpurun_out/san_$tool.log; tail -4 gpurun_out/san_$tool.log
+done
