@@ -60,11 +60,11 @@ def test_replay_parity_gpu_vs_reference_scores():
     g5, sd = load_golden("mycnn5_xtestinput.npz")
     rec = _record(g)
     model = tskd_b200.B200MyCNN.from_reference(sd).to("cuda:0")
-    rows = S.replay(model, rec, subject_id=194, age=65.0)               # ONE batched predict()
+    rows = S.replay(model, rec, subject_id=194, age=65.0, on_gpu=False)  # host-assembled windows, ONE batched predict()
     assert len(rows) == 1615 and rows[0][0] == 194 and rows[1][1] - rows[0][1] == 60.0
     probs = np.array([r[2] for r in rows])
     assert rel_err(probs, g["probs"]) <= 1e-4                            # vs the unmodified reference
-    rows_mb = S.replay(model, rec, subject_id=194, age=65.0, micro_batch=16)   # BATCHSIZE = 16 (config.cfg:26)
+    rows_mb = S.replay(model, rec, subject_id=194, age=65.0, micro_batch=16, on_gpu=False)   # BATCHSIZE = 16 (config.cfg:26)
     # micro-batches of 16 take the single-launch small-window kernel, the full batch the general path
     assert rel_err(np.array([r[2] for r in rows_mb]), probs) <= 1e-6
     # logits on identical x_arr: GPU vs golden vs oracle per-window loop
@@ -152,7 +152,7 @@ def test_replay_on_gpu_equals_host_assembled_replay():
     _, sd = load_golden("mycnn5_xtestinput.npz")
     rec = _record(g)
     model = tskd_b200.B200MyCNN.from_reference(sd).to("cuda:0")
-    rows_h = S.replay(model, rec, subject_id=194)
+    rows_h = S.replay(model, rec, subject_id=194, on_gpu=False)
     rows_d = S.replay(model, rec, subject_id=194, on_gpu=True)
     assert len(rows_h) == len(rows_d) == 1615
     assert [r[:2] for r in rows_h] == [r[:2] for r in rows_d]

@@ -157,11 +157,12 @@ def assemble_windows_gpu(record: NumericsRecord, device="cuda", dtype=None):
 
 
 def replay(model, record: NumericsRecord, subject_id: int, age: float = 65.0,
-           micro_batch: int = 0, on_gpu: bool = False) -> List[Tuple[int, float, float]]:
+           micro_batch: int = 0, on_gpu: bool = True) -> List[Tuple[int, float, float]]:
     """Score every window of the record and return the rows the reference INSERTs into
     ``predictions`` (db/init.sql:24-28): (SUBJECT_ID, PRED_TIME [s since record start], RISK_SCORE).
     ``micro_batch`` = windows per predict() call (0 = all at once); NaN scores are dropped
-    like predictStream.py:171.  ``on_gpu`` builds the windows on the device (assemble_windows_gpu)."""
+    like predictStream.py:171.  ``on_gpu`` (default) builds the windows on the device (assemble_windows_gpu); ``on_gpu=False`` assembles them with
+    the numpy restatement on the host and uploads them (what the tests use as the oracle of the device path)."""
     import torch
     rows: List[Tuple[int, float, float]] = []
     if on_gpu:                                                   # raw record -> windows -> scores without leaving the device
