@@ -168,3 +168,21 @@ def test_prep_rejects_bad_arguments():
         S.assemble_windows_gpu(rec, "cuda:0")
     with pytest.raises(RuntimeError):
         S.assemble_windows_gpu(_synthetic_record(9, 700, 1.0), "cpu")
+
+
+def test_prep_c_abi_argument_errors_need_no_gpu():
+    """b2cnn_prep_windows validates shapes, pointers and the workspace before any CUDA call."""
+    import ctypes
+    from tskd_b200 import capi
+    lib = capi.load_library()
+    cfg = capi.PrepConfig(S.N_CHANNELS, S.WINDOW_POINTS, S.GRID_S, S.SMOOTH_S, S.STRIDE_S)
+    sel = np.array([0, 1], dtype=np.int32); g = np.ones(7); b = np.zeros(7)
+    args = lambda raw, xo, ws, wsb: (raw, 1000, 7, sel.ctypes.data, 2, g.ctypes.data, b.ctypes.data, 1.0, ctypes.byref(cfg),
+                                     xo, 0, None, ws, wsb, None)
+    assert lib.b2cnn_prep_windows(*args(None, None, None, 0)) == capi.EINVAL            # null pointers
+    assert "null" in capi.last_error()
+    need = lib.b2cnn_prep_workspace_bytes(1000, 1.0, 2, ctypes.byref(cfg))
+    assert need > 0
+    assert lib.b2cnn_prep_windows(*args(0x1000, 0x2000, 0x3000, need - 1)) == capi.ESTATE   # workspace too small
+    bad = (0x1000, 1000, 7, sel.ctypes.data, 2, g.ctypes.data, b.ctypes.data, 1.0, ctypes.byref(cfg), 0x2000, 7, None, 0x3000, need, None)
+    assert lib.b2cnn_prep_windows(*bad) == capi.EINVAL                                   # dtype
