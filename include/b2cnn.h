@@ -151,6 +151,34 @@ int b2cnn_prep_windows(const int16_t *raw, int64_t n_samples, int32_t n_sig, con
                        const double *gains, const double *baselines, double fs, const b2cnn_prep_config *cfg,
                        void *x_out, int dtype, double *t0_out, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* ---- The same two steps as a STREAM: per-patient device ring buffers ----
+ * Replaces the per-trigger Python loop of bin/predictStream.py:70-156 (one row per patient, B = 1 each, numpy
+ * assembly on the host) by device-resident state for P patients: every trigger appends the new samples of all
+ * patients (b2cnn_ring_push), the grid points whose 180 s window is now complete are finalised and forward-filled
+ * (bin/processStream.py:62-123,196-208), and the [P][n_channels][window_points] batch of the 600 s window that just
+ * completed is written for ONE b2cnn_forward call.  Pushing a record trigger by trigger reproduces
+ * b2cnn_prep_windows on the whole record bit-for-bit (tests/test_stream.py).
+ *   n_sig        signals per sample frame (columns of the pushed arrays)
+ *   fs           sampling rate shared by the ring's patients (1/60 Hz for MIMIC numerics)
+ *   new_samples  DEVICE pointer [n_patients][n_new][n_sig]: B2CNN_SAMPLES_ADC16 = int16 ADC units as in a WFDB
+ *                format-16 file (-32768 = missing; gain / baseline from b2cnn_ring_set_signals), or
+ *                B2CNN_SAMPLES_F64 = physical values as fp64 (NaN = missing) -- what bin/sendStream.py:59-64 publishes
+ *   emitted      host int: 1 when x_out was written (from the 10th trigger on), 0 while the first window fills
+ * One push may carry at most stride_s seconds of samples.  The ring owns its device buffers; b2cnn_ring_push allocates
+ * nothing and is asynchronous on `stream`. */
+enum { B2CNN_SAMPLES_ADC16 = 0, B2CNN_SAMPLES_F64 = 1 };
+typedef struct b2cnn_ring b2cnn_ring;
+int b2cnn_ring_create(const b2cnn_prep_config *cfg, int32_t n_patients, int32_t n_sig, double fs, int32_t device,
+                      b2cnn_ring **out);
+void b2cnn_ring_destroy(b2cnn_ring *ring);
+int b2cnn_ring_reset(b2cnn_ring *ring, void *stream);
+/* sel[n_sel]: frame columns of the model's signals for this patient (position i -> model channel i);
+ * gains / baselines: host arrays [n_sig] or NULL (physical input). */
+int b2cnn_ring_set_signals(b2cnn_ring *ring, int32_t patient, const int32_t *sel, int32_t n_sel, const double *gains,
+                           const double *baselines, void *stream);
+int b2cnn_ring_push(b2cnn_ring *ring, const void *new_samples, int sample_kind, int64_t n_new, void *x_out, int dtype,
+                    int32_t *emitted, int64_t *window_index, double *t0_seconds, void *stream);
+
 const char *b2cnn_last_error(void);
 const char *b2cnn_version(void);
 

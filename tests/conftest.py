@@ -36,6 +36,15 @@ def rel_err(got, want):
     return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-6))
 
 
+def rel_err_elem(got, want, floor_frac=1e-2):
+    """PER-ELEMENT relative error: max_i |got_i - want_i| / max(|want_i|, floor_frac * max|want|).  The floor only
+    keeps logits that happen to sit next to zero from dividing by ~0 (they are judged against 1 % of the batch scale)."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    den = np.maximum(np.abs(want), floor_frac * max(np.abs(want).max(), 1e-30))
+    return float((np.abs(got - want) / den).max())
+
+
 @pytest.fixture(scope="session")
 def golden5():
     return load_golden("mycnn5_xtestinput.npz")

@@ -8,7 +8,9 @@ What is executed is the reference's own code: ``bin/models.py`` (class ``MyCNN``
 ``forward``), the shipped checkpoints ``model/MyCNN{2,3,4,5}.pth``, the fixture
 ``explore_output/X.TESTINPUT`` and (verbatim, with stub modules for the absent ``wfdb`` /
 ``pyspark`` imports) ``bin/utils.py``'s ``create_batch`` / ``get_arr`` / ``run_model``.
-Nothing from this repo's oracle/ or product code is used to produce the expected values.
+Nothing from this repo's product code is used to produce the expected values; the streaming fixtures
+(section 4) get their 5-second grids from pandas (oracle/stream_pandas.py: the reference notebook's own
+``resample`` / ``rolling`` calls), never from the numpy restatement or the CUDA kernels they pin.
 """
 import os
 import sys
@@ -158,17 +160,54 @@ def golden_stretched():
 
 
 # ---------------------------------------------------------------- 4. streaming replay (configs[4])
-def golden_replay():
-    """The shipped numerics record p000194 (7 signals @ 1/60 Hz, 1625 samples) replayed through the
-    restated window logic (tskd_b200/stream.py builds x_arr); expected scores = the UNMODIFIED
-    reference model called once per window exactly as predictStream.py:154-162 does."""
-    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+def _synthetic_record(seed, n, fs, n_sig=7, p_missing=0.2, lead_gap=0, dead=None):
+    """The synthetic numerics records of tests/test_stream.py (same generator, same seeds)."""
     import tskd_b200.stream as S
+    rng = np.random.default_rng(seed)
+    names = ["HR", "PULSE", "junk A", "RESP", "SpO2", "NBPSys", "CVP"][:n_sig]
+    raw = rng.integers(-500, 3000, size=(n, n_sig)).astype(np.int16)
+    raw[rng.random((n, n_sig)) < p_missing] = -32768
+    if lead_gap:
+        raw[:lead_gap, 0] = -32768
+    if dead is not None:
+        raw[:, dead] = -32768
+    gains = rng.choice([1.0, 10.0, 12.5], size=n_sig)
+    bases = rng.integers(-5, 5, size=n_sig).astype(np.float64)
+    return S.NumericsRecord(tuple(names), gains, bases, fs, raw)
+
+
+SYNTH_RECORDS = [(1, 1625, 1 / 60, {}), (2, 4000, 1.0, {"p_missing": 0.5}), (3, 900, 1.0, {"lead_gap": 400}),
+                 (4, 2500, 0.2, {"dead": 1}), (5, 700, 1.0, {"p_missing": 0.0}), (6, 50000, 1.0, {"p_missing": 0.9}),
+                 (7, 640, 1.0, {"n_sig": 2}), (8, 3000, 0.1, {"p_missing": 0.4})]
+
+
+def golden_replay():
+    """The shipped numerics record p000194 (7 signals @ 1/60 Hz, 1625 samples): the 5-second grid is built with
+    PANDAS -- the reference's own offline calls ``resample('5S').first()`` / ``rolling('3min').mean()``
+    (bin/explore_torch.ipynb:402,405) + the streaming job's ffill / bfill / fillna(0) (bin/processStream.py:62-123),
+    oracle/stream_pandas.py -- cut into the 600 s / 60 s windows of bin/predictStream.py:245-259, and scored by the
+    UNMODIFIED reference model called once per window exactly as predictStream.py:154-162 does.  Nothing of the
+    product (nor of the numpy restatement) produces an expected value here; only the WFDB byte reader is shared,
+    and it is pinned by the header's checksums."""
+    root = os.path.dirname(os.path.dirname(OUT))
+    sys.path.insert(0, root)
+    import tskd_b200.stream as S
+    from oracle import stream_pandas as P
     d = f"{REF}/data/waveform/physionet.org/files/mimic3wdb-matched/1.0/p00/p000194"
     rec = S.NumericsRecord.from_wfdb_files(f"{d}/p000194-2112-05-23-14-34n.hea", f"{d}/3400942n.dat")
     csum = [int(np.int16(rec.raw[:, i].astype(np.int64).sum() & 0xffff)) for i in range(rec.raw.shape[1])]
     assert csum == [3240, 20492, 29088, 10310, -27206, -29717, -28780], csum      # header checksums
-    x, t0 = S.assemble_windows(rec)
+    sel = S.selected_signals(rec)
+    phys = rec.physical
+    grids = np.stack([P.grid_notebook(phys[:, s_], rec.fs) for s_ in sel])
+    grids_spark = np.stack([P.grid_spark(phys[:, s_], rec.fs) for s_ in sel])
+    assert np.abs(grids - grids_spark).max() <= 1e-9                             # lattice record: both pipelines agree
+    n_grid = grids.shape[1]
+    starts = np.arange(0, n_grid - 120 + 1, 12)
+    x = np.zeros((len(starts), 10, 120))
+    for ch in range(len(sel)):
+        x[:, ch, :] = np.lib.stride_tricks.sliding_window_view(grids[ch], 120)[starts]
+    t0 = starts * 5.0
     m = load_ckpt(5)
     probs, logits = [], []
     with torch.no_grad():
@@ -181,8 +220,21 @@ def golden_replay():
     np.savez_compressed(os.path.join(OUT, "p000194_replay.npz"), raw=rec.raw, names=np.array(rec.names),
                         gains=rec.gains, baselines=rec.baselines, fs=np.array(rec.fs),
                         logits=np.array(logits, dtype=np.float32), probs=np.array(probs, dtype=np.float64),
-                        t0=t0, x_first=x[0], x_last=x[-1])
-    print("replay:", x.shape, "selected", [rec.names[i] for i in S.selected_signals(rec)], logits[:3], probs[-1])
+                        t0=t0, x_first=x[0], x_last=x[-1], grids=grids, grids_unfilled=np.stack(
+                            [P.grid_notebook(phys[:, s_], rec.fs, fill=False) for s_ in sel]))
+    print("replay:", x.shape, "selected", [rec.names[i] for i in sel], logits[:3], probs[-1])
+    # synthetic records (gaps, dead signals, several sampling rates): the streaming aggregate written with pandas
+    out = {}
+    for seed, n, fs, kw in SYNTH_RECORDS:
+        r = _synthetic_record(seed, n, fs, **kw)
+        ph = r.physical
+        sl = S.selected_signals(r)
+        g = np.stack([P.grid_spark(ph[:, s_], r.fs) for s_ in sl])
+        out[f"grid{seed}"] = g
+        if fs <= 0.2:       # at most one sample per 5-second bin: the notebook's resample().first() is the same thing
+            assert np.abs(g - np.stack([P.grid_notebook(ph[:, s_], r.fs) for s_ in sl])).max() <= 1e-9
+    np.savez_compressed(os.path.join(OUT, "stream_synth_grids.npz"), **out)
+    print("synthetic grids:", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 import tskd_b200
-from conftest import load_golden, rel_err
+from conftest import load_golden, rel_err, rel_err_elem
 from oracle import mycnn_c
 from oracle import mycnn_torch as O
 
@@ -239,7 +239,8 @@ def test_conv_act_affine_pool_vs_torch_nn(act, geom):
 def test_full_size_properties():
     """[4096, 3, 75000] bf16 (BASELINE.json configs[1]): size-independent properties --
     equivariance under a permutation of the windows, prefix consistency, duplicate windows give
-    bit-identical logits -- plus an oracle check on a 24-window subsample."""
+    bit-identical logits -- plus the oracle on ALL 4096 windows (chunks of 128 through torch-CPU, ~10-40 s of host
+    time), judged per element."""
     ref, m = _pair("mycnn5", 3, 75000)
     B = 4096
     x = tskd_b200.synth.make_windows(B, 3, 75000, "normal", seed=1234, dtype=torch.bfloat16, device=DEV)
@@ -250,9 +251,12 @@ def test_full_size_properties():
     perm = torch.randperm(B, device=DEV)
     assert torch.equal(m.predict(x[perm], ages[perm]), y[perm])
     assert torch.equal(m.predict(x[:1000], ages[:1000]), y[:1000])
-    idx = torch.arange(0, B, B // 24, device=DEV)[:24]
-    want = O.ref_independent(ref, x[idx].float().cpu(), ages[idx].cpu()).numpy()
-    assert rel_err(y[idx].cpu().numpy(), want) <= TOL
+    yh = y.cpu().numpy()
+    worst = 0.0
+    for b0 in range(0, B, 128):
+        want = O.ref_independent(ref, x[b0:b0 + 128].float().cpu(), ages[b0:b0 + 128].cpu()).numpy()
+        worst = max(worst, rel_err_elem(yh[b0:b0 + 128], want))
+    assert worst <= TOL, worst
 
 
 def test_single_launch_small_window_kernel(golden5):

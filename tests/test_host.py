@@ -56,12 +56,21 @@ def test_fails_loudly_without_gpu():
 
 
 def test_product_never_imports_oracle():
+    """No import / include / dlopen of anything under oracle/ from the shipped package (comments may cite the checker)."""
+    import re
     pkg = os.path.join(ROOT, "time-series-kafka-demo_b200")
+    bad = re.compile(r"""^\s*(from|import)\s+\.*oracle\b|__import__\(\s*['"]oracle|import_module\(\s*['"]oracle|"""
+                     r"""#\s*include\s*["<][^">]*oracle|CDLL\([^)]*oracle|libmycnn_ref""", re.M)
+    n = 0
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("the oracle", "").replace("oracle/mycnn_torch.py", ""), f
+                assert not bad.search(src), f
+                n += 1
+    assert n > 10
+    for f in ("tskd_b200.py",):
+        assert not bad.search(open(os.path.join(ROOT, f)).read()), f
 
 
 def test_state_dict_contract(golden5):
@@ -119,6 +128,34 @@ def test_restricted_unpickler_rejects_foreign_globals(tmp_path):
         pickle.dump(os.system, f)
     with pytest.raises(Exception):
         tskd_b200.load_reference_checkpoint(str(p))
+
+
+class _EvalPayload:
+    def __reduce__(self):
+        return (eval, ("__import__('os').getpid()",))
+
+
+class _GetattrPayload:
+    def __reduce__(self):
+        return (getattr, ("abc", "upper"))
+
+
+@pytest.mark.parametrize("payload", [_EvalPayload, _GetattrPayload])
+@pytest.mark.parametrize("zipfile", [False, True])
+def test_restricted_unpickler_rejects_builtins_and_torch_prefix(tmp_path, payload, zipfile):
+    """builtins.eval / getattr (and anything merely *under* torch. or numpy.) must not unpickle --
+    the allowlist is exact (module, name) pairs, not prefixes."""
+    import pickle
+    p = tmp_path / "evil.pth"
+    torch.save(payload(), str(p), _use_new_zipfile_serialization=zipfile)
+    with pytest.raises(pickle.UnpicklingError):
+        tskd_b200.load_reference_checkpoint(str(p))
+    from tskd_b200 import checkpoint
+    up = checkpoint._Unpickler.__new__(checkpoint._Unpickler)
+    for mod, name in (("builtins", "eval"), ("torch.serialization", "load"), ("numpy", "load"), ("_codecs", "encode"),
+                      ("torch._utils", "_rebuild_tensor_v2x")):
+        with pytest.raises(pickle.UnpicklingError):
+            checkpoint._Unpickler.find_class(up, mod, name)
 
 
 def test_synth_is_deterministic():

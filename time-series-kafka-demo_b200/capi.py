@@ -18,13 +18,15 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 MODE_INDEPENDENT, MODE_SEQUENCE = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_TENSORCORE = 0, 1, 2
 FLAG_AFFINE = 1
+SAMPLES_ADC16, SAMPLES_F64 = 0, 1
 
-# every symbol include/b2cnn.h declares (tests/test_capi_symbols.py checks the list)
+# every symbol include/b2cnn.h declares (tests/test_host.py::test_library_exports_every_declared_symbol checks the list)
 SYMBOLS = ("b2cnn_l_out", "b2cnn_weight_count", "b2cnn_create", "b2cnn_destroy",
            "b2cnn_set_weights", "b2cnn_workspace_bytes", "b2cnn_forward", "b2cnn_forward_host",
            "b2cnn_features", "b2cnn_set_option", "b2cnn_get_option", "b2cnn_last_launch_count",
            "b2cnn_last_path", "b2cnn_last_stage_ms", "b2cnn_last_error", "b2cnn_version",
-           "b2cnn_prep_window_count", "b2cnn_prep_workspace_bytes", "b2cnn_prep_windows")
+           "b2cnn_prep_window_count", "b2cnn_prep_workspace_bytes", "b2cnn_prep_windows",
+           "b2cnn_ring_create", "b2cnn_ring_destroy", "b2cnn_ring_reset", "b2cnn_ring_set_signals", "b2cnn_ring_push")
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -85,6 +87,14 @@ def load_library() -> ctypes.CDLL:
     lib.b2cnn_prep_windows.argtypes = [c_vp, c_i64, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.c_double, pcfg,
                                        c_vp, c_int, c_vp, c_vp, c_i64, c_vp]
     lib.b2cnn_prep_windows.restype = c_int
+    c_i32 = ctypes.c_int32
+    lib.b2cnn_ring_create.argtypes = [pcfg, c_i32, c_i32, ctypes.c_double, c_i32, ctypes.POINTER(c_vp)]; lib.b2cnn_ring_create.restype = c_int
+    lib.b2cnn_ring_destroy.argtypes = [c_vp]; lib.b2cnn_ring_destroy.restype = None
+    lib.b2cnn_ring_reset.argtypes = [c_vp, c_vp]; lib.b2cnn_ring_reset.restype = c_int
+    lib.b2cnn_ring_set_signals.argtypes = [c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]; lib.b2cnn_ring_set_signals.restype = c_int
+    lib.b2cnn_ring_push.argtypes = [c_vp, c_vp, c_int, c_i64, c_vp, c_int, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64),
+                                    ctypes.POINTER(ctypes.c_double), c_vp]
+    lib.b2cnn_ring_push.restype = c_int
     lib.b2cnn_last_error.argtypes = []; lib.b2cnn_last_error.restype = ctypes.c_char_p
     lib.b2cnn_version.argtypes = []; lib.b2cnn_version.restype = ctypes.c_char_p
     _lib = lib

@@ -4,8 +4,8 @@
 ``__main__.MyCNN`` (written by ``torch.save(model, path, _use_new_zipfile_serialization=False)``,
 bin/explore_torch.ipynb:995,3234,3285).  Unpickling them needs *a* class of that name; the
 reference satisfies it with ``from models import MyCNN`` (bin/predictStream.py:8).  Here a
-restricted unpickler maps that one global to an inert ``nn.Module`` stub and only lets
-through the globals the audited pickles contain, so loading does not depend on
+restricted unpickler maps that one global to an inert ``nn.Module`` stub and lets through an
+exact (module, name) allowlist of the globals the audited pickles contain -- nothing else, so loading does not depend on
 ``bin/models.py`` and the architecture is read from the unpickled sub-modules, not assumed.
 """
 from __future__ import annotations
@@ -29,16 +29,30 @@ class PickledMyCNN(nn.Module):
                            "wrap it with B200MyCNN.from_reference(...)")
 
 
-_ALLOWED_PREFIXES = ("torch.", "collections", "__builtin__", "builtins", "numpy", "_codecs")
+# Exact (module, name) allowlist: the GLOBAL opcodes of the four audited checkpoints (pickletools over
+# model/MyCNN{2,3,4,5}.pth) plus the storage classes a plain state_dict file may name.  Anything else --
+# builtins.eval, os.system, getattr ... -- raises UnpicklingError instead of being imported.
+_ALLOWED_GLOBALS = {
+    ("collections", "OrderedDict"),
+    ("torch._utils", "_rebuild_tensor_v2"),
+    ("torch._utils", "_rebuild_parameter"),
+    ("torch", "FloatStorage"), ("torch", "DoubleStorage"), ("torch", "HalfStorage"), ("torch", "BFloat16Storage"),
+    ("torch", "LongStorage"), ("torch", "IntStorage"),
+    ("torch.nn.modules.conv", "Conv1d"),
+    ("torch.nn.modules.pooling", "MaxPool1d"),
+    ("torch.nn.modules.dropout", "Dropout"),
+    ("torch.nn.modules.linear", "Linear"),
+    ("torch.nn.modules.rnn", "LSTM"),
+}
 
 
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if name == "MyCNN":
+        if (module, name) == ("__main__", "MyCNN"):
             return PickledMyCNN
-        if module == "__builtin__" and name == "set":
+        if (module, name) in (("__builtin__", "set"), ("builtins", "set")):
             return set
-        if module.startswith(_ALLOWED_PREFIXES) or module in ("torch", "collections"):
+        if (module, name) in _ALLOWED_GLOBALS:
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"global {module}.{name} is not allowed in a MyCNN checkpoint")
 

@@ -28,6 +28,25 @@ static int cuda_fail(cudaError_t e, const char *what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
     } while (0)
 
+// Every entry point that touches the handle's device switches to it for the duration of the call only and
+// restores the caller's current device on every exit path (a forward on cuda:1 must not leave the calling
+// thread on cuda:1 -- later `device="cuda"` allocations of the host framework would land on the wrong GPU).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) { prev = -1; return; }
+        if (prev != dev) err = cudaSetDevice(dev); else prev = -1;     // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define DEVICE_GUARD(dev)                   \
+    DeviceGuard guard__(dev);               \
+    if (guard__.err != cudaSuccess) return cuda_fail(guard__.err, "cudaSetDevice")
+
 struct b2cnn_handle {
     b2cnn_config cfg;
     Dims d;
@@ -112,7 +131,62 @@ extern "C" int b2cnn_prep_windows(const int16_t *raw, int64_t n_samples, int32_t
                                 workspace_bytes, reinterpret_cast<cudaStream_t>(stream), &err);
     return rc == B2CNN_OK ? rc : fail(rc, std::string("b2cnn_prep_windows: ") + err);
 }
-extern "C" const char *b2cnn_version(void) { return "b2cnn 0.2 (sm_100a; tcgen05 fused bf16 path, fp32 streaming path, generic path, device preprocessing)"; }
+// ---- streaming form: per-patient device ring buffers (b2cnn_prep.cu) ----
+struct b2cnn_ring { Ring *r; int device; };
+
+extern "C" int b2cnn_ring_create(const b2cnn_prep_config *cfg, int32_t n_patients, int32_t n_sig, double fs, int32_t device,
+                                 b2cnn_ring **out) {
+    if (!cfg || !out) return fail(B2CNN_EINVAL, "b2cnn_ring_create: null argument");
+    *out = nullptr;
+    int dev = device;
+    if (dev < 0) CU_TRY(cudaGetDevice(&dev));
+    DEVICE_GUARD(dev);
+    const char *err = "";
+    Ring *r = nullptr;
+    const int rc = ring_create(cfg, n_patients, n_sig, fs, dev, &r, &err);
+    if (rc != B2CNN_OK) return fail(rc, std::string("b2cnn_ring_create: ") + err);
+    b2cnn_ring *h = new (std::nothrow) b2cnn_ring{r, dev};
+    if (!h) { ring_destroy(r); return fail(B2CNN_ESTATE, "out of host memory"); }
+    *out = h;
+    return B2CNN_OK;
+}
+extern "C" void b2cnn_ring_destroy(b2cnn_ring *h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    ring_destroy(h->r);
+    delete h;
+}
+extern "C" int b2cnn_ring_reset(b2cnn_ring *h, void *stream) {
+    if (!h) return fail(B2CNN_EINVAL, "b2cnn_ring_reset: null argument");
+    DEVICE_GUARD(h->device);
+    const char *err = "";
+    const int rc = ring_reset(h->r, reinterpret_cast<cudaStream_t>(stream), &err);
+    return rc == B2CNN_OK ? rc : fail(rc, std::string("b2cnn_ring_reset: ") + err);
+}
+extern "C" int b2cnn_ring_set_signals(b2cnn_ring *h, int32_t patient, const int32_t *sel, int32_t n_sel, const double *gains,
+                                      const double *baselines, void *stream) {
+    if (!h) return fail(B2CNN_EINVAL, "b2cnn_ring_set_signals: null argument");
+    DEVICE_GUARD(h->device);
+    const char *err = "";
+    const int rc = ring_set_signals(h->r, patient, sel, n_sel, gains, baselines, reinterpret_cast<cudaStream_t>(stream), &err);
+    return rc == B2CNN_OK ? rc : fail(rc, std::string("b2cnn_ring_set_signals: ") + err);
+}
+extern "C" int b2cnn_ring_push(b2cnn_ring *h, const void *new_samples, int sample_kind, int64_t n_new, void *x_out, int dtype,
+                               int32_t *emitted, int64_t *window_index, double *t0_seconds, void *stream) {
+    if (!h) return fail(B2CNN_EINVAL, "b2cnn_ring_push: null argument");
+    if (sample_kind != B2CNN_SAMPLES_ADC16 && sample_kind != B2CNN_SAMPLES_F64)
+        return fail(B2CNN_EINVAL, "b2cnn_ring_push: sample_kind must be B2CNN_SAMPLES_ADC16 or B2CNN_SAMPLES_F64");
+    DEVICE_GUARD(h->device);
+    const char *err = "";
+    int em = 0;
+    const int rc = ring_push(h->r, new_samples, sample_kind == B2CNN_SAMPLES_ADC16, n_new, x_out, dtype, &em, window_index,
+                             t0_seconds, reinterpret_cast<cudaStream_t>(stream), &err);
+    if (rc != B2CNN_OK) return fail(rc, std::string("b2cnn_ring_push: ") + err);
+    if (emitted) *emitted = em;
+    return B2CNN_OK;
+}
+
+extern "C" const char *b2cnn_version(void) { return "b2cnn 0.3 (sm_100a; tcgen05 fused bf16 path, fp32 streaming path, generic path, device preprocessing + patient ring buffers)"; }
 
 extern "C" int b2cnn_create(const b2cnn_config *cfg, b2cnn_handle **out) {
     if (!cfg || !out) return fail(B2CNN_EINVAL, "b2cnn_create: null argument");
@@ -134,7 +208,7 @@ extern "C" int b2cnn_create(const b2cnn_config *cfg, b2cnn_handle **out) {
     }
     int dev = cfg->device;
     if (dev < 0) CU_TRY(cudaGetDevice(&dev));
-    CU_TRY(cudaSetDevice(dev));
+    DEVICE_GUARD(dev);
     b2cnn_handle *h = new (std::nothrow) b2cnn_handle();
     if (!h) return fail(B2CNN_ESTATE, "out of host memory");
     h->cfg = *cfg; h->d = d; h->device = dev;
@@ -150,7 +224,7 @@ extern "C" int b2cnn_create(const b2cnn_config *cfg, b2cnn_handle **out) {
 
 extern "C" void b2cnn_destroy(b2cnn_handle *h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     tc_release(h->tc);
     cudaFree(h->d_blob); cudaFree(h->d_wih0T);
     for (int i = 0; i < 3; ++i)
@@ -174,7 +248,7 @@ extern "C" int b2cnn_set_weights(b2cnn_handle *h, const float *blob, int64_t n, 
         return fail(B2CNN_EINVAL, buf);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    CU_TRY(cudaSetDevice(h->device));
+    DEVICE_GUARD(h->device);
     const Dims &d = h->d;
     CU_TRY(cudaMemcpyAsync(h->d_blob, blob, sizeof(float) * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     // conv weights + affine -> host copy for the kernel-parameter constant bank
@@ -341,7 +415,7 @@ extern "C" int b2cnn_forward(b2cnn_handle *h, const void *x, int dtype, int64_t 
     if (rc) return rc;
     if (!workspace || workspace_bytes < b2cnn_workspace_bytes(h, B, mode))
         return fail(B2CNN_ESTATE, "b2cnn_forward: workspace missing or smaller than b2cnn_workspace_bytes()");
-    CU_TRY(cudaSetDevice(h->device));
+    DEVICE_GUARD(h->device);
     return forward_device(h, x, dtype, B, age, n_age, mode, apply_sigmoid, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -349,7 +423,7 @@ extern "C" int b2cnn_features(b2cnn_handle *h, const void *x, int dtype, int64_t
     if (!h || !x || !feats) return fail(B2CNN_EINVAL, "b2cnn_features: null argument");
     if (!h->weights_set) return fail(B2CNN_ESTATE, "b2cnn_features: weights not set");
     if (B < 1) return fail(B2CNN_EINVAL, "b2cnn_features: B < 1");
-    CU_TRY(cudaSetDevice(h->device));
+    DEVICE_GUARD(h->device);
     const char *err = "";
     int n;
     if (use_tc(h, dtype, B, B2CNN_MODE_INDEPENDENT) && tc_can_emit_features(h->tc)) {
@@ -397,7 +471,7 @@ extern "C" int b2cnn_forward_host(b2cnn_handle *h, const void *x_host, int dtype
                                   int64_t n_age, int mode, int apply_sigmoid, float *out_host) {
     int rc = check_call(h, x_host, dtype, B, age_host, n_age, mode, out_host);
     if (rc) return rc;
-    CU_TRY(cudaSetDevice(h->device));
+    DEVICE_GUARD(h->device);
     const Dims &d = h->d;
     const size_t esz = dtype == B2CNN_DTYPE_BF16 ? 2 : 4;
     const size_t win_bytes = (size_t)d.C * d.W * esz;

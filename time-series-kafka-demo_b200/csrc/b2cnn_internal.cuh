@@ -118,6 +118,17 @@ int prep_windows(const int16_t *raw, int64_t n_samples, int n_sig, const int *se
                  const double *baselines, double fs, const b2cnn_prep_config *cfg, void *x_out, int dtype, double *t0_out,
                  void *workspace, int64_t ws_bytes, cudaStream_t st, const char **err);
 
+// streaming form of the same preprocessing: per-patient device ring buffers (b2cnn_prep.cu)
+struct Ring;
+int ring_create(const b2cnn_prep_config *cfg, int n_patients, int n_sig, double fs, int device, Ring **out, const char **err);
+void ring_destroy(Ring *r);
+int ring_device(const Ring *r);
+int ring_reset(Ring *r, cudaStream_t st, const char **err);
+int ring_set_signals(Ring *r, int patient, const int *sel, int n_sel, const double *gains, const double *baselines,
+                     cudaStream_t st, const char **err);
+int ring_push(Ring *r, const void *new_samples, int in_is_adc, int64_t n_new, void *x_out, int dtype, int *emitted,
+              int64_t *window_out, double *t0_out, cudaStream_t st, const char **err);
+
 void launch_transpose_wih(const float *wih0, float *wih0T, int L, cudaStream_t st);
 
 }  // namespace b2cnn

@@ -94,7 +94,12 @@ class B200MyCNN(nn.Module):
         return self.conv1.weight.device
 
     def _weights_version(self):
-        return tuple(p._version for p in self.parameters()) + (str(self._device()),)
+        # in-place edits (p.copy_(), p.mul_(), p.data.fill_() ...) bump Tensor._version; swapping a
+        # parameter object or moving the module changes the id / device entries
+        ps = self.__dict__.get("_vparams")
+        if ps is None:
+            ps = self.__dict__["_vparams"] = tuple(self.parameters())
+        return tuple(p._version for p in ps) + (id(ps[0]), ps[0].device)
 
     def packed_weights(self) -> torch.Tensor:
         """The blob b2cnn_set_weights() takes (include/b2cnn.h), on the parameters' device."""
@@ -115,14 +120,38 @@ class B200MyCNN(nn.Module):
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
         self.__dict__["_dirty"] = True
+        self.__dict__["_vparams"] = None          # .to() may replace the Parameter objects
         return r
+
+    # The native handle, the CDLL and the workspace tensor never travel with a copy or a pickle
+    # (the reference saves whole-module pickles, bin/explore_torch.ipynb:3234): a restored / copied
+    # module rebuilds its own handle lazily on its first forward.
+    _NATIVE_STATE = ("_handle", "_handle_device", "_lib", "_ws", "_ws_need", "_synced_version", "_vparams", "_dirty")
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in self._NATIVE_STATE:
+            st.pop(k, None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self.__dict__.update(_handle=None, _handle_device=None, _ws=None, _synced_version=None, _dirty=True)
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__setstate__(copy.deepcopy(self.__getstate__(), memo))
+        return new
 
     def sync_weights(self):
         self.__dict__["_dirty"] = True
         self._ensure_handle()
 
     def _ensure_handle(self):
-        if not self.__dict__.get("_dirty", True) and self._handle is not None:
+        if not self.__dict__.get("_dirty", True) and self._handle is not None \
+                and self._synced_version == self._weights_version():
             return self._lib, self._handle                      # fast path of the hot call
         dev = self._device()
         if dev.type != "cuda":

@@ -2,9 +2,10 @@
 
 The reference's live path is Kafka -> Spark -> ``write_to_mysql`` (bin/predictStream.py:53-192),
 which calls ``model(x_arr, a_arr)`` once per patient row with B=1.  None of that plumbing exists
-here (no Kafka / Spark / MySQL in this image, and it is out of scope); this module replays a WFDB
-numerics record through a *restatement of the window logic* and hands the whole micro-batch of
-windows to ONE ``predict()`` call -- the "batched GPU dispatch" the north-star asks for:
+here (no Kafka / Spark / MySQL in this image, and it is out of scope); this module replays WFDB
+numerics records through the window logic ON THE DEVICE (csrc/b2cnn_prep.cu) and hands whole micro-batches of
+windows to ONE ``predict()`` call -- the "batched GPU dispatch" the north-star asks for -- either a complete record at
+once (``replay``) or trigger by trigger for many patients through device ring buffers (``replay_stream``):
 
   sendStream.py:39-72      one message per (sample, signal): value = [signal_index, sample];
                            the index is the position in the record's selected signal list
@@ -72,54 +73,11 @@ def selected_signals(record: NumericsRecord) -> List[int]:
     return [i for i, n in enumerate(record.names) if n in CHANNEL_NAMES]
 
 
-def smooth_to_grid(samples: np.ndarray, fs: float) -> np.ndarray:
-    """processStream.py:196-208 + :62-123 for one signal: value at grid time tau (multiples of 5 s)
-    = mean of the samples with time in (tau-180, tau]; NaN samples are skipped; then ffill, bfill,
-    0-fill."""
-    period = 1.0 / fs
-    t = np.arange(samples.shape[0]) * period
-    n_grid = int(np.floor(t[-1] / GRID_S)) + 1
-    tau = np.arange(n_grid) * GRID_S
-    lo = np.searchsorted(t, tau - SMOOTH_S, side="right")
-    hi = np.searchsorted(t, tau, side="right")
-    ok = ~np.isnan(samples)
-    csum = np.concatenate([[0.0], np.cumsum(np.where(ok, samples, 0.0))])
-    ccnt = np.concatenate([[0], np.cumsum(ok)])
-    cnt = ccnt[hi] - ccnt[lo]
-    with np.errstate(invalid="ignore", divide="ignore"):
-        g = (csum[hi] - csum[lo]) / cnt
-    g[cnt == 0] = np.nan
-    idx = np.where(~np.isnan(g), np.arange(n_grid), -1)          # forward fill
-    np.maximum.accumulate(idx, out=idx)
-    g = np.where(idx >= 0, g[np.maximum(idx, 0)], np.nan)
-    if np.isnan(g).any():                                         # back fill, then zeros
-        good = np.where(~np.isnan(g))[0]
-        if good.size:
-            g[:good[0]] = g[good[0]]
-        g = np.nan_to_num(g, nan=0.0)
-    return g
-
-
-def assemble_windows(record: NumericsRecord) -> Tuple[np.ndarray, np.ndarray]:
-    """All model inputs of the replay: x_arr [n_windows, 10, 120] float64 (as predictStream.py:105
-    builds it) and the window start times in seconds."""
-    phys = record.physical
-    sel = selected_signals(record)
-    grids = [smooth_to_grid(phys[:, s], record.fs) for s in sel]
-    n_grid = min(len(g) for g in grids)
-    step = STRIDE_S // GRID_S
-    starts = np.arange(0, n_grid - WINDOW_POINTS + 1, step)
-    x = np.zeros((len(starts), N_CHANNELS, WINDOW_POINTS), dtype=np.float64)    # absent signals: zeros (:131)
-    for ch, g in enumerate(grids):                                              # message index == ch
-        x[:, ch, :] = np.lib.stride_tricks.sliding_window_view(g[:n_grid], WINDOW_POINTS)[starts]
-    return x, starts * float(GRID_S)
-
-
 def assemble_windows_gpu(record: NumericsRecord, device="cuda", dtype=None):
     """The same model inputs built ON THE DEVICE by libb2cnn's b2cnn_prep_windows (csrc/b2cnn_prep.cu): the raw
     int16 record goes up once (a few KB), smoothing / filling / window assembly run as four small kernels and the
-    [n_windows, 10, 120] batch is written straight into the tensor predict() reads.  `assemble_windows` above is
-    the oracle of this path.  Returns (x [n_windows, 10, 120] f32|bf16 on `device`, t0 [n_windows] f64 seconds)."""
+    [n_windows, 10, 120] batch is written straight into the tensor predict() reads.  oracle/stream_np.py (pinned
+    against pandas) is the checker of this path.  Returns (x [n_windows, 10, 120] f32|bf16 on `device`, t0 [n_windows] f64 seconds)."""
     import ctypes
 
     import torch
@@ -156,31 +114,151 @@ def assemble_windows_gpu(record: NumericsRecord, device="cuda", dtype=None):
     return x, t0
 
 
+def _model_device(model):
+    """The CUDA device a (possibly not yet migrated) B200MyCNN lives on: a model built the documented way
+    (``B200MyCNN.from_reference(...).eval()``, no ``.to('cuda')``) migrates on its first forward."""
+    ensure = getattr(model, "_ensure_handle", None)
+    if ensure is not None:
+        ensure()
+    return next(model.parameters()).device
+
+
+def _rows(rows, subject_id, t0, prob):
+    for tt, p in zip(t0, prob):
+        if not np.isnan(p):                                      # predictStream.py:171 drops NaN results
+            rows.append((int(subject_id), float(tt), float(p)))
+
+
 def replay(model, record: NumericsRecord, subject_id: int, age: float = 65.0,
-           micro_batch: int = 0, on_gpu: bool = True) -> List[Tuple[int, float, float]]:
+           micro_batch: int = 0) -> List[Tuple[int, float, float]]:
     """Score every window of the record and return the rows the reference INSERTs into
     ``predictions`` (db/init.sql:24-28): (SUBJECT_ID, PRED_TIME [s since record start], RISK_SCORE).
-    ``micro_batch`` = windows per predict() call (0 = all at once); NaN scores are dropped
-    like predictStream.py:171.  ``on_gpu`` (default) builds the windows on the device (assemble_windows_gpu); ``on_gpu=False`` assembles them with
-    the numpy restatement on the host and uploads them (what the tests use as the oracle of the device path)."""
-    import torch
+    The raw record goes to the device once; smoothing, filling, window assembly (b2cnn_prep_windows) and scoring
+    never leave it.  ``micro_batch`` = windows per predict() call (0 = all at once)."""
     rows: List[Tuple[int, float, float]] = []
-    if on_gpu:                                                   # raw record -> windows -> scores without leaving the device
-        xg, t0g = assemble_windows_gpu(record, device=next(model.parameters()).device)
-        mb = micro_batch or max(len(xg), 1)
-        t0 = t0g.cpu().numpy()
-        for b0 in range(0, len(xg), mb):
-            prob = model.predict(xg[b0:b0 + mb], age, return_prob=True).cpu().numpy()
-            for tt, p in zip(t0[b0:b0 + mb], prob):
-                if not np.isnan(p):
-                    rows.append((int(subject_id), float(tt), float(p)))
+    xg, t0g = assemble_windows_gpu(record, device=_model_device(model))
+    if len(xg) == 0:
         return rows
-    x, t0 = assemble_windows(record)
-    mb = micro_batch or len(x)
-    for b0 in range(0, len(x), mb):
-        xb = torch.from_numpy(x[b0:b0 + mb]).float()            # predictStream.py:155
-        prob = model.predict(xb, age, return_prob=True).cpu().numpy()
-        for tt, p in zip(t0[b0:b0 + mb], prob):
-            if not np.isnan(p):
-                rows.append((int(subject_id), float(tt), float(p)))
+    mb = micro_batch or len(xg)
+    t0 = t0g.cpu().numpy()
+    for b0 in range(0, len(xg), mb):
+        prob = model.predict(xg[b0:b0 + mb], age, return_prob=True).cpu().numpy()
+        _rows(rows, subject_id, t0[b0:b0 + mb], prob)
+    return rows
+
+
+class PatientRing:
+    """Device-resident streaming state for P patients (libb2cnn's b2cnn_ring_*, csrc/b2cnn_prep.cu): what
+    bin/predictStream.py:70-156 rebuilds on the host for every patient row of every trigger.  ``push`` appends one
+    trigger's samples for all patients and returns the ``[P, 10, 120]`` batch of the window that just completed
+    (``None`` while the first 600 s fill) -- the input of ONE ``predict()`` call per trigger."""
+
+    def __init__(self, n_patients: int, n_sig: int, fs: float, device="cuda", dtype=None):
+        import ctypes
+
+        import torch
+
+        from . import capi
+        self._lib = capi.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PatientRing needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = dtype or torch.float32
+        if self.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError("dtype must be torch.float32 or torch.bfloat16")
+        self.n_patients, self.n_sig, self.fs = int(n_patients), int(n_sig), float(fs)
+        cfg = capi.PrepConfig(N_CHANNELS, WINDOW_POINTS, GRID_S, SMOOTH_S, STRIDE_S)
+        h = ctypes.c_void_p()
+        capi.check(self._lib.b2cnn_ring_create(ctypes.byref(cfg), self.n_patients, self.n_sig, self.fs, self.device.index,
+                                               ctypes.byref(h)), "b2cnn_ring_create")
+        self._h = h
+        self.x = torch.empty((self.n_patients, N_CHANNELS, WINDOW_POINTS), dtype=self.dtype, device=self.device)
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None:
+            self._lib.b2cnn_ring_destroy(h)
+
+    __del__ = close
+
+    def set_signals(self, patient: int, sel, gains=None, baselines=None):
+        """``sel``: frame columns of the model's signals for this patient (position i -> model channel i, the
+        message index of bin/sendStream.py:59-64); ``gains`` / ``baselines`` [n_sig] for ADC input."""
+        from . import capi
+        sel = np.ascontiguousarray(sel, dtype=np.int32)
+        g = None if gains is None else np.ascontiguousarray(gains, dtype=np.float64)
+        b = None if baselines is None else np.ascontiguousarray(baselines, dtype=np.float64)
+        capi.check(self._lib.b2cnn_ring_set_signals(self._h, int(patient), sel.ctypes.data, len(sel),
+                                                    None if g is None else g.ctypes.data,
+                                                    None if b is None else b.ctypes.data, None), "b2cnn_ring_set_signals")
+
+    def set_record_signals(self, patient: int, record: NumericsRecord):
+        self.set_signals(patient, selected_signals(record), record.gains, record.baselines)
+
+    def reset(self):
+        from . import capi
+        capi.check(self._lib.b2cnn_ring_reset(self._h, None), "b2cnn_ring_reset")
+
+    def push(self, new_samples):
+        """``new_samples`` [P, n_new, n_sig]: int16 ADC units (WFDB format 16, -32768 = missing) or float64 physical
+        values (NaN = missing), host or device.  Returns ``(x [P,10,120] on the device, window_index, t0_seconds)`` or
+        ``None`` while the first window is still filling.  The returned tensor is reused by the next push."""
+        import ctypes
+
+        import torch
+
+        from . import capi
+        t = torch.as_tensor(new_samples)
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        if t.dtype == torch.int16:
+            kind = capi.SAMPLES_ADC16
+        else:
+            kind, t = capi.SAMPLES_F64, t.to(torch.float64)
+        if t.shape[0] != self.n_patients or t.shape[2] != self.n_sig:
+            raise RuntimeError(f"expected samples [{self.n_patients}, n_new, {self.n_sig}], got {tuple(t.shape)}")
+        t = t.to(self.device).contiguous()
+        em, widx, t0 = ctypes.c_int32(0), ctypes.c_int64(-1), ctypes.c_double(0.0)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            capi.check(self._lib.b2cnn_ring_push(self._h, t.data_ptr(), kind, t.shape[1], self.x.data_ptr(),
+                                                 0 if self.dtype == torch.float32 else 1, ctypes.byref(em), ctypes.byref(widx),
+                                                 ctypes.byref(t0), st), "b2cnn_ring_push")
+            t.record_stream(torch.cuda.current_stream())
+        return (self.x, int(widx.value), float(t0.value)) if em.value else None
+
+
+def replay_stream(model, records: Sequence[NumericsRecord], subject_ids: Sequence[int], ages=65.0,
+                  samples_per_trigger: int = 0) -> List[Tuple[int, float, float]]:
+    """The live path's shape (bin/predictStream.py:263: one foreachBatch per 60 s trigger) with the B = 1 per-row loop
+    turned into the batched dispatch: all records (same sampling rate and length, one per patient) are fed trigger by
+    trigger into a PatientRing and every trigger costs ONE ``predict()`` over ``[P, 10, 120]``.  Returns the
+    ``predictions`` rows (db/init.sql:24-28) of all patients, trigger-major."""
+    import torch
+    P = len(records)
+    fs, n, n_sig = records[0].fs, records[0].raw.shape[0], records[0].raw.shape[1]
+    if any(r.fs != fs or r.raw.shape != (n, n_sig) for r in records):
+        raise RuntimeError("replay_stream: the records of one ring share sampling rate, length and signal count")
+    dev = _model_device(model)
+    ring = PatientRing(P, n_sig, fs, device=dev)
+    for p, r in enumerate(records):
+        ring.set_record_signals(p, r)
+    per = samples_per_trigger or max(1, int(round(STRIDE_S * fs)))
+    raw = torch.from_numpy(np.stack([np.ascontiguousarray(r.raw, dtype=np.int16) for r in records])).to(dev)
+    age_t = torch.as_tensor(ages, dtype=torch.float32).reshape(-1)
+    if age_t.numel() not in (1, P):
+        raise RuntimeError(f"ages must be a scalar or have {P} elements")
+    rows: List[Tuple[int, float, float]] = []
+    for i0 in range(0, n, per):
+        out = ring.push(raw[:, i0:i0 + per])
+        if out is None:
+            continue
+        x, _, t0 = out
+        prob = model.predict(x, age_t, return_prob=True).cpu().numpy()    # one batched call per trigger
+        for p in range(P):
+            if not np.isnan(prob[p]):                                     # predictStream.py:171 drops NaN results
+                rows.append((int(subject_ids[p]), t0, float(prob[p])))
+    ring.close()
     return rows
