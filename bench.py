@@ -169,9 +169,11 @@ def build_cpu_model():
     return O.make_ref(O.stretched(O.ARCH_MYCNN5, C, W), seed=0), "port"
 
 
-def _cpu_worker(idx, conn):
+def _cpu_worker(idx, conn, counter):
     """One single-threaded scorer: per-window model(x[i:i+1], age[i:i+1]) under no_grad
-    (bin/predictStream.py:154-157), PyTorch-CPU fp32.  Stays alive across steps."""
+    (bin/predictStream.py:154-157), PyTorch-CPU fp32.  Stays alive across steps.  Within a step the workers
+    pull windows from ONE shared counter until the step's total is scored, so a worker the container's CPU
+    quota throttles does not decide the step time by itself."""
     try:
         torch.set_num_threads(1)
         import tskd_b200
@@ -187,15 +189,21 @@ def _cpu_worker(idx, conn):
             cmd = conn.recv()
             if cmd[0] == "stop":
                 break
-            _, count, t_at = cmd
+            _, t_at = cmd
             while time.perf_counter() < t_at:        # CLOCK_MONOTONIC: one time base for all processes
                 time.sleep(0.0005)
             t0 = time.perf_counter()
+            done = 0
             with torch.no_grad():
-                for k in range(count):
-                    i = k % n
+                while True:
+                    with counter.get_lock():
+                        if counter.value <= 0:
+                            break
+                        counter.value -= 1
+                    i = done % n
                     model(x[i:i + 1], ages[i:i + 1])
-            conn.send((t0, time.perf_counter(), count))
+                    done += 1
+            conn.send((t0, time.perf_counter(), done))
     except Exception as e:                            # never leave the parent waiting
         try:
             conn.send(("error", repr(e)))
@@ -206,19 +214,20 @@ def _cpu_worker(idx, conn):
 class CpuPool:
     """All host cores on the reference's path.  One torch process with N intra-op threads is SLOWER than one
     thread on this per-window call (137 vs 461 windows/s measured on a 64-core box: the ops are too small to
-    split), so the cores are used the way the path shards: one single-threaded scorer process per CPU, each
-    looping predictStream-style over its own windows.  The workers are spawned once and stay alive; the
-    number of ACTIVE workers is calibrated (hyper-threads / memory bandwidth can make fewer workers faster)."""
+    split), so the cores are used the way the path shards: one single-threaded scorer process per usable CPU, each
+    looping predictStream-style over windows.  The workers are spawned once and stay alive; the number of ACTIVE
+    workers is calibrated (hyper-threads / memory bandwidth / a cgroup quota can make fewer workers faster)."""
 
     def __init__(self, max_workers=None):
         import torch.multiprocessing as mp
         self.cap, self.n_aff, self.quota = usable_cpus()
         n = min(self.cap, max_workers or 128)
         ctx = mp.get_context("spawn")
+        self.counter = ctx.Value("q", 0)
         self.procs, self.conns = [], []
         for i in range(n):
             a, b = ctx.Pipe()
-            p = ctx.Process(target=_cpu_worker, args=(i, b), daemon=True)
+            p = ctx.Process(target=_cpu_worker, args=(i, b, self.counter), daemon=True)
             p.start()
             self.procs.append(p); self.conns.append(a)
         self.kind = None
@@ -231,11 +240,13 @@ class CpuPool:
             self.kind = msg[1]
         self.active = n
 
-    def step(self, active, count):
-        """`active` workers score `count` windows each, started together; returns (windows, wall_s, rates)."""
+    def step(self, active, total):
+        """`active` workers score `total` windows between them, started together; returns (windows, wall_s, per-worker counts)."""
+        with self.counter.get_lock():
+            self.counter.value = int(total)
         t_at = time.perf_counter() + 0.02
         for c in self.conns[:active]:
-            c.send(("run", count, t_at))
+            c.send(("run", t_at))
         res = []
         for c in self.conns[:active]:
             if not c.poll(1800):
@@ -244,8 +255,10 @@ class CpuPool:
             if r[0] == "error":
                 raise RuntimeError(f"CPU worker failed: {r[1]}")
             res.append(r)
-        wall = max(r[1] for r in res) - min(r[0] for r in res)
-        return sum(r[2] for r in res), wall, [r[2] / (r[1] - r[0]) for r in res]
+        wall = max(r[1] for r in res) - t_at
+        done = sum(r[2] for r in res)
+        assert done == int(total), (done, total)
+        return done, wall, [r[2] for r in res]
 
     def calibrate(self, seconds=1.5):
         """Pick the active-worker count with the best whole-pool throughput (candidates: all usable CPUs, 1/2, 1/4)."""
@@ -253,13 +266,13 @@ class CpuPool:
         cands = sorted({n, max(1, n // 2), max(1, n // 4)}, reverse=True)
         table = []
         for a in cands:
-            _, w0, r0 = self.step(a, 2)                                   # short probe -> windows for ~`seconds`
-            per = max(2, int(seconds * statistics.median(r0)))
-            wins, wall, _ = self.step(a, per)
+            wins, w0, _ = self.step(a, 4 * a)                              # short probe -> windows for ~`seconds`
+            total = max(2 * a, int(seconds * wins / w0))
+            wins, wall, _ = self.step(a, total)
             table.append({"workers": a, "windows_per_s": wins / wall})
         best = max(table, key=lambda t: t["windows_per_s"])
         self.active = best["workers"]
-        self.rate_per_worker = best["windows_per_s"] / best["workers"]
+        self.rate = best["windows_per_s"]
         return table
 
     def close(self):
@@ -275,26 +288,26 @@ class CpuPool:
 
 
 def cpu_reference_run(steps, warmup, seconds_total):
-    """K timed steps (after W warm-up steps) of the reference path on the calibrated pool; every step each active
-    worker scores the same fixed number of windows, sized so that the timed region lasts ~`seconds_total`
-    (>= 5 s per worker).  Returns the numbers both bench legs report."""
+    """K timed steps (after W warm-up steps) of the reference path on the calibrated pool; every step the active
+    workers score the same fixed number of windows between them, sized so that the timed region lasts
+    ~`seconds_total` (>= 5 s).  Returns the numbers both bench legs report."""
     pool = CpuPool()
     try:
         table = pool.calibrate()
         per_step_s = max(0.25, seconds_total / max(1, steps))
-        per = max(2, int(round(per_step_s * pool.rate_per_worker)))
+        total = max(2 * pool.active, int(round(per_step_s * pool.rate)))
         for _ in range(max(1, warmup)):
-            pool.step(pool.active, per)
-        wins = 0; wall = 0.0; rates = []
+            pool.step(pool.active, total)
+        wins = 0; wall = 0.0; counts = []; step_rates = []
         for _ in range(steps):
-            n, dt, r = pool.step(pool.active, per)
-            wins += n; wall += dt; rates.append(r)
-        per_worker = [statistics.mean(col) for col in zip(*rates)]
+            n, dt, c = pool.step(pool.active, total)
+            wins += n; wall += dt; counts.append(c); step_rates.append(n / dt)
+        per_worker = [sum(col) / wall for col in zip(*counts)]
         return {"value": wins / wall, "windows": wins, "seconds": wall, "workers": pool.active, "kind": pool.kind,
-                "windows_per_worker_step": per, "calibration": table,
+                "windows_per_step": total, "calibration": table,
                 "usable_cpus": pool.cap, "affinity_cpus": pool.n_aff, "cgroup_quota": pool.quota,
                 "per_worker_windows_per_s": {"min": min(per_worker), "median": statistics.median(per_worker), "max": max(per_worker)},
-                "step_windows_per_s": {"min": min(sum(r) for r in rates), "max": max(sum(r) for r in rates)}}
+                "step_windows_per_s": {"min": min(step_rates), "median": statistics.median(step_rates), "max": max(step_rates)}}
     finally:
         pool.close()
 
@@ -304,7 +317,7 @@ def cpu_baseline_block(r, steps):
             "tests/golden/make_golden.py does" if r["kind"] == "reference" else "oracle/mycnn_torch.py (restatement of bin/models.py)")
     return {"value": r["value"], "unit": UNIT, "cores": r["workers"], "kind": r["kind"],
             "sample": (f"{r['windows']} windows in {r['seconds']:.1f} s: {steps} steps x {r['workers']} persistent single-thread worker "
-                       f"processes x {r['windows_per_worker_step']} windows, per-window model(x[i:i+1], age[i:i+1]) loop under no_grad "
+                       f"processes sharing {r['windows_per_step']} windows per step (pulled from one counter), per-window model(x[i:i+1], age[i:i+1]) loop under no_grad "
                        f"(bin/predictStream.py:154-157) on {what}, torch {torch.__version__} CPU fp32"),
             "usable_cpus": r["usable_cpus"], "affinity_cpus": r["affinity_cpus"], "cgroup_quota": r["cgroup_quota"],
             "os_cpu_count": os.cpu_count(), "calibration": r["calibration"],

@@ -21,18 +21,25 @@ for line in out.splitlines():
         if m:
             ins.append((int(m.group(1), 16), m.group(2).strip()))
 best = None
+cands = []
 for i, (a, t) in enumerate(ins):
     m = re.search(r"BRA(?:\.U)?\s+(?:[!U]*P\d,\s*)?0x([0-9a-f]+)", t)
     if m and int(m.group(1), 16) < a:
         tgt = int(m.group(1), 16)
         body = [x for x in ins if tgt <= x[0] <= a]
         n2 = sum("FFMA2" in x[1] for x in body)
-        if n2 >= 80 and (best is None or len(body) < len(best[1])):     # the tightest loop that holds the packed math
-            best = (n2, body)
-n2, body = best
-ops = collections.Counter()
-for a, t in body:
-    t = re.sub(r"^@!?U?P\d\s+", "", t)
-    ops[t.split()[0].split(".")[0]] += 1
-print(f"loop body: {len(body)} instructions, {n2} FFMA2")
-print(", ".join(f"{k} {v}" for k, v in ops.most_common()))
+        if n2 >= 80:
+            cands.append((n2, body))
+# every loop that holds the packed math, innermost first (the unrolled main loop and the run-time tail loop)
+seen = []
+for n2, body in sorted(cands, key=lambda c: len(c[1])):
+    if any(body[0][0] <= b[0][0] and b[-1][0] <= body[-1][0] for b in seen):
+        continue                                        # an outer loop around one already printed
+    seen.append(body)
+    ops = collections.Counter()
+    for a, t in body:
+        t = re.sub(r"^@!?U?P\d\s+", "", t)
+        ops[t.split()[0].split(".")[0]] += 1
+    steps = max(1, round(n2 / 57))
+    print(f"loop body @0x{body[0][0]:x}: {len(body)} instructions, {n2} FFMA2  (~{steps} steps -> {len(body) / steps:.0f} instructions per step)")
+    print("   " + ", ".join(f"{k} {v}" for k, v in ops.most_common()))

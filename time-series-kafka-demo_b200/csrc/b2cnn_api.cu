@@ -296,14 +296,41 @@ extern "C" int b2cnn_set_weights(b2cnn_handle *h, const float *blob, int64_t n, 
     return B2CNN_OK;
 }
 
+// Which kernels a (dtype, B, mode) call takes decides its scratch: the streaming tensor-core kernels need the range
+// partials [slices][B][64] (+ [B][64] gates for a sequence scan) and a few ints per window; only the generic and the
+// unfused tensor-core paths round-trip feature rows [B][L] through HBM.
+struct WsLayout { int64_t feats, partial, gates, tc, total; int ks_ws; };
+
+static bool use_tc(b2cnn_handle *h, int dtype, int64_t B, int mode);
+
+static WsLayout ws_layout(b2cnn_handle *h, int64_t B, int mode, int dtype) {
+    const Dims &d = h->d;
+    WsLayout w;
+    const int ks = choose_ksplit(B, d.L, h->num_sms);
+    w.ks_ws = tc_partial_slices(h->tc) > ks ? tc_partial_slices(h->tc) : ks;
+    bool streaming = false;
+    if (dtype >= 0 && h->opt_path != B2CNN_PATH_GENERIC) {
+        if (dtype == B2CNN_DTYPE_F32) streaming = h->opt_stream && tc_stream_supported(h->tc, d, dtype);
+        else streaming = use_tc(h, dtype, B, mode) && tc_fused_supported(h->tc, d, dtype);
+    }
+    w.feats = streaming ? 0 : align_up(B * d.L * 4, 256);
+    w.partial = align_up((int64_t)w.ks_ws * B * kGates * 4, 256);
+    w.gates = align_up(B * kGates * 4, 256);
+    w.tc = tc_workspace_bytes(h->tc, d, B);
+    w.total = w.feats + w.partial + w.gates + w.tc;
+    return w;
+}
+
+// dtype-blind size: enough for whatever path a call may take (the generic path's feature rows included)
 extern "C" int64_t b2cnn_workspace_bytes(b2cnn_handle *h, int64_t B, int mode) {
     if (!h || B < 1) return -1;
-    (void)mode;
-    int ks = choose_ksplit(B, h->d.L, h->num_sms);
-    if (tc_partial_slices(h->tc) > ks) ks = tc_partial_slices(h->tc);
-    int64_t bytes = align_up(B * h->d.L * 4, 256) + align_up((int64_t)ks * B * kGates * 4, 256) + align_up(B * kGates * 4, 256);
-    bytes += tc_workspace_bytes(h->tc, h->d, B);
-    return bytes;
+    return ws_layout(h, B, mode, -1).total;
+}
+
+// exact size for windows of `dtype`: 307 MB smaller at [4096,3,75000] bf16, where the features never leave the SM
+extern "C" int64_t b2cnn_workspace_bytes_for(b2cnn_handle *h, int64_t B, int mode, int dtype) {
+    if (!h || B < 1 || (dtype != B2CNN_DTYPE_F32 && dtype != B2CNN_DTYPE_BF16)) return -1;
+    return ws_layout(h, B, mode, dtype).total;
 }
 
 static bool use_tc(b2cnn_handle *h, int dtype, int64_t B, int mode) {
@@ -315,13 +342,13 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
                           int mode, int apply_sigmoid, float *out, void *ws, int64_t ws_bytes, cudaStream_t st) {
     const Dims &d = h->d;
     const int ks = choose_ksplit(B, d.L, h->num_sms);
-    const int ks_ws = tc_partial_slices(h->tc) > ks ? tc_partial_slices(h->tc) : ks;   // as in b2cnn_workspace_bytes
+    const WsLayout wl = ws_layout(h, B, mode, dtype);
+    if (ws_bytes < wl.total) return fail(B2CNN_ESTATE, "b2cnn_forward: workspace smaller than b2cnn_workspace_bytes_for()");
     char *base = (char *)ws;
-    float *feats = (float *)base; base += align_up(B * d.L * 4, 256);
-    float *partial = (float *)base; base += align_up((int64_t)ks_ws * B * kGates * 4, 256);
-    float *gates = (float *)base; base += align_up(B * kGates * 4, 256);
+    float *feats = wl.feats ? (float *)base : nullptr; base += wl.feats;
+    float *partial = (float *)base; base += wl.partial;
+    float *gates = (float *)base; base += wl.gates;
     void *tc_ws = base;
-    (void)ws_bytes;
     const char *err = "";
     int launches = 0;
     const bool tc = use_tc(h, dtype, B, mode);
@@ -355,8 +382,7 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
         if (n < 0) return fail(B2CNN_ECUDA, std::string("fp32 stream kernel: ") + err);
         launches += n;
         if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
-        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, reinterpret_cast<const int *>(tc_ws), gates, B, age, n_age,
-                                            apply_sigmoid, out, st, &err)
+        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, B, age, n_age, apply_sigmoid, out, st, &err)
                   : launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
         if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
         launches += n;
@@ -372,8 +398,7 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
         if (n < 0) return fail(B2CNN_ECUDA, std::string("tensor-core fused kernel: ") + err);
         launches += n;
         if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
-        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, reinterpret_cast<const int *>(tc_ws), gates, B, age, n_age,
-                                            apply_sigmoid, out, st, &err)
+        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, B, age, n_age, apply_sigmoid, out, st, &err)
                   : launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
         if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
         launches += n;
@@ -413,8 +438,8 @@ extern "C" int b2cnn_forward(b2cnn_handle *h, const void *x, int dtype, int64_t 
                              int mode, int apply_sigmoid, float *out, void *workspace, int64_t workspace_bytes, void *stream) {
     int rc = check_call(h, x, dtype, B, age, n_age, mode, out);
     if (rc) return rc;
-    if (!workspace || workspace_bytes < b2cnn_workspace_bytes(h, B, mode))
-        return fail(B2CNN_ESTATE, "b2cnn_forward: workspace missing or smaller than b2cnn_workspace_bytes()");
+    if (!workspace || workspace_bytes < ws_layout(h, B, mode, dtype).total)
+        return fail(B2CNN_ESTATE, "b2cnn_forward: workspace missing or smaller than b2cnn_workspace_bytes_for()");
     DEVICE_GUARD(h->device);
     return forward_device(h, x, dtype, B, age, n_age, mode, apply_sigmoid, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -482,7 +507,7 @@ extern "C" int b2cnn_forward_host(b2cnn_handle *h, const void *x_host, int dtype
         if (chunk < 1) chunk = 1;
         if (chunk > B) chunk = B;
     }
-    const int64_t ws_bytes = b2cnn_workspace_bytes(h, chunk, mode);
+    const int64_t ws_bytes = ws_layout(h, chunk, mode, dtype).total;
     rc = ensure_host_staging(h, (size_t)chunk * win_bytes, B, (size_t)ws_bytes);
     if (rc) return rc;
     CU_TRY(cudaMemcpyAsync(h->st_age, age_host, sizeof(float) * n_age, cudaMemcpyHostToDevice, h->s_copy));

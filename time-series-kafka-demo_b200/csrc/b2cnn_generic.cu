@@ -50,20 +50,26 @@ __global__ void __launch_bounds__(256, 2) frontend_kernel(const __grid_constant_
     constexpr int NA = NQ + K2 - 1;
     const int tid = threadIdx.x;
     const int W = p.d.W;
-    const int p0 = blockIdx.x * p.tile_p;
-    const int tp = min(p.tile_p, p.d.L - p0);
-    const int nq = (tp - 1) * PS + PK;
-    const int nj = nq + K2 - 1;
-    const int nt = (nj - 1) * PS + PK;
-    const int ni = nt + K1 - 1;
-    const int i0 = p0 * PS * PS;               // first input sample of the receptive field
-    const int n_runs = (nj + RUN - 1) / RUN;
-    const int n_runs2 = (tp + 1) / 2;
     const int act = p.d.act, aff = p.d.has_affine;
+    const bool gate_mode = p.gate_part != nullptr;
+    __shared__ float gred[4][kGates];
+    const int tile_lo = gate_mode ? blockIdx.x * p.tiles_per_slice : blockIdx.x;
+    const int tile_hi = gate_mode ? min(p.n_tiles, tile_lo + p.tiles_per_slice) : tile_lo + 1;
 
     const int nwin = p.win_count ? *p.win_count : p.B;
     for (int wi = blockIdx.y; wi < nwin; wi += gridDim.y) {
         const int b = p.win_list ? p.win_list[wi] : wi;
+        float gacc = 0.f;                      // gate mode: thread (gate g = tid & 63, position slice tid >> 6)
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        const int p0 = tile * p.tile_p;
+        const int tp = min(p.tile_p, p.d.L - p0);
+        const int nq = (tp - 1) * PS + PK;
+        const int nj = nq + K2 - 1;
+        const int nt = (nj - 1) * PS + PK;
+        const int ni = nt + K1 - 1;
+        const int i0 = p0 * PS * PS;           // first input sample of the receptive field
+        const int n_runs = (nj + RUN - 1) / RUN;
+        const int n_runs2 = (tp + 1) / 2;
         // ---- stage 1: input tile -> smem (fp32) ------------------------------------------
         const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * W + i0;
         for (int c = 0; c < C; ++c) {
@@ -160,12 +166,28 @@ __global__ void __launch_bounds__(256, 2) frontend_kernel(const __grid_constant_
                         for (int u = 1; u < PK; ++u)
                             v = max_nan(v, apply_act(conv_epilogue(acc2[PS * pp + u], p.cw.b2, p.cw.s2, p.cw.t2, 1), act));
                     }
-                    p.feats[(int64_t)b * p.sB + (int64_t)(p0 + pl) * p.sP] = v;
+                    if (gate_mode) xs[pl] = v;     // xs is free after stage 2: the tile's features stay on chip
+                    else p.feats[(int64_t)b * p.sB + (int64_t)(p0 + pl) * p.sP] = v;
                 }
             }
         }
-        // no barrier needed here: the next iteration's stage 1 only writes xs (whose readers
+        // no barrier needed here in feature mode: the next iteration's stage 1 only writes xs (whose readers
         // all passed the stage-2 barrier) and its own barrier orders a1 reuse.
+        if (gate_mode) {
+            __syncthreads();
+            const int g = tid & 63;
+            for (int pl = tid >> 6; pl < tp; pl += 4) gacc = fmaf(xs[pl], __ldg(p.wih0T + (int64_t)(p0 + pl) * kGates + g), gacc);
+            __syncthreads();                   // xs is rewritten by the next tile's stage 1
+        }
+      }
+        if (gate_mode) {                       // fixed-order sum of the four position slices -> gate_part[slice][b][g]
+            gred[tid >> 6][tid & 63] = gacc;
+            __syncthreads();
+            if (tid < kGates)
+                p.gate_part[((int64_t)blockIdx.x * p.B + b) * kGates + tid] =
+                    tile_lo < tile_hi ? (gred[0][tid] + gred[1][tid]) + (gred[2][tid] + gred[3][tid]) : 0.f;
+            __syncthreads();
+        }
     }
 }
 
@@ -258,14 +280,36 @@ int launch_frontend_generic(const Dims &d, const ConvWeights &cw, const void *x,
     return launch_frontend_generic_listed(d, cw, x, dtype, B, feats, sB, sP, nullptr, nullptr, st, num_sms, err);
 }
 
+static int launch_frontend_impl(const Dims &d, const ConvWeights &cw, const void *x, int dtype, int64_t B, float *feats,
+                                int64_t sB, int64_t sP, const int *win_list, const int *win_count, const float *wih0T,
+                                float *gate_part, int gate_slices, cudaStream_t st, int num_sms, const char **err);
+
 // win_list / win_count (device memory, may be null): recompute only the listed windows; the
 // count is read on the device, so an empty list costs one almost-empty launch and no host sync.
 int launch_frontend_generic_listed(const Dims &d, const ConvWeights &cw, const void *x, int dtype,
                                    int64_t B, float *feats, int64_t sB, int64_t sP, const int *win_list,
                                    const int *win_count, cudaStream_t st, int num_sms, const char **err) {
+    return launch_frontend_impl(d, cw, x, dtype, B, feats, sB, sP, win_list, win_count, nullptr, nullptr, 0, st, num_sms, err);
+}
+
+// The exception path of the streaming tensor-core kernels in ONE launch and without a feature buffer: for every
+// listed window the exact features of a slice of positions are multiplied by W_ih_l0^T on the spot and written as
+// gate_part[slice][b][64] -- the very rows of the range-partial buffer the head kernel sums (the streaming kernel's
+// rows for these windows hold NaN garbage and are overwritten; unused slices are zero-filled).
+int launch_frontend_generic_gates_listed(const Dims &d, const ConvWeights &cw, const void *x, int dtype, int64_t B,
+                                         const float *wih0T, float *gate_part, int gate_slices, const int *win_list,
+                                         const int *win_count, cudaStream_t st, int num_sms, const char **err) {
+    if (!gate_part || !wih0T || gate_slices < 1 || !win_list || !win_count) { *err = "gate mode: null argument"; return -1; }
+    return launch_frontend_impl(d, cw, x, dtype, B, nullptr, 0, 0, win_list, win_count, wih0T, gate_part, gate_slices, st, num_sms, err);
+}
+
+static int launch_frontend_impl(const Dims &d, const ConvWeights &cw, const void *x, int dtype, int64_t B, float *feats,
+                                int64_t sB, int64_t sP, const int *win_list, const int *win_count, const float *wih0T,
+                                float *gate_part, int gate_slices, cudaStream_t st, int num_sms, const char **err) {
     FrontParams p;
     p.x = x; p.feats = feats; p.sB = sB; p.sP = sP; p.B = (int)B; p.d = d; p.cw = cw;
     p.win_list = win_list; p.win_count = win_count;
+    p.gate_part = gate_part; p.wih0T = wih0T; p.gate_slices = gate_slices; p.tiles_per_slice = 1;
     // 508 final positions -> <= 256 thread-runs of 4 pooled outputs in stage 2 (see header).
     const int kTile = 508;
     p.tile_p = d.L < kTile ? d.L : kTile;
@@ -277,12 +321,17 @@ int launch_frontend_generic_listed(const Dims &d, const ConvWeights &cw, const v
     p.a1_stride = padi(nj + d.PS * 2 + d.PK + d.K2 + 8) + 1;
     const size_t smem = (size_t)(d.C * p.xs_stride + kCMid * p.a1_stride) * sizeof(float);
     if (smem > 220 * 1024) { *err = "front end: tile does not fit shared memory (in_channels too large)"; return -1; }
-    int gy = (2 * num_sms + p.n_tiles - 1) / p.n_tiles;
+    int gx = p.n_tiles;
+    if (gate_part) {                            // every slice of the partial buffer gets a CTA (empty ones write zeros)
+        p.tiles_per_slice = (p.n_tiles + gate_slices - 1) / gate_slices;
+        gx = gate_slices;
+    }
+    int gy = (2 * num_sms + gx - 1) / gx;
     if (gy > B) gy = (int)B;
     if (win_list && gy > 16) gy = 16;          // the exception path: few windows expected
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
-    dim3 grid(p.n_tiles, gy);
+    dim3 grid(gx, gy);
 
 #define B2_TRY(CT, K1_, K2_, PK_, PS_)                                                         \
     if ((CT == 0 || d.C == CT) && d.K1 == K1_ && d.K2 == K2_ && d.PK == PK_ && d.PS == PS_)   \
@@ -298,6 +347,7 @@ int launch_frontend_generic_listed(const Dims &d, const ConvWeights &cw, const v
     B2_TRY(0, 10, 5, 3, 2)
     B2_TRY(0, 5, 5, 2, 2)
 #undef B2_TRY
+    if (gate_part) { *err = "gate mode needs a templated conv geometry"; return -1; }
     if (dtype == B2CNN_DTYPE_F32) return launch_one(frontend_any_kernel<float>, p, grid, smem, st, err);
     return launch_one(frontend_any_kernel<__nv_bfloat16>, p, grid, smem, st, err);
 }

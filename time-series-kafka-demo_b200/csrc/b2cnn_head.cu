@@ -159,12 +159,11 @@ head_independent_kernel(const float *__restrict__ gates0, HeadWeights hw, const 
 }
 
 // Independent windows, reduction fused in: 16 lanes per window (lane u = hidden unit u), 16 windows per CTA.
-// gates0[b][g] = (sum_k partial[k][b][g] + b_ih[g]) + b_hh[g] in the same fixed order as reduce_gates_kernel,
-// unless the window was flagged by a tensor-core front end, in which case its exactly recomputed row of
-// `gates_listed` is taken.  The arithmetic per window is that of head_independent_kernel, term for term.
+// gates0[b][g] = (sum_k partial[k][b][g] + b_ih[g]) + b_hh[g] in the same fixed order as reduce_gates_kernel
+// (windows a tensor-core front end flagged had their partial rows overwritten by the exact re-computation before
+// this kernel runs).  The arithmetic per window is that of head_independent_kernel, term for term.
 __global__ void __launch_bounds__(256)
-head_reduce_independent_kernel(const float *__restrict__ part, int slices, const int *__restrict__ flags,
-                               const float *__restrict__ gates_listed, HeadWeights hw, const float *__restrict__ age,
+head_reduce_independent_kernel(const float *__restrict__ part, int slices, HeadWeights hw, const float *__restrict__ age,
                                int64_t n_age, float coef, int apply_sigmoid, float *__restrict__ out, int64_t B) {
     __shared__ float s_w1[kHidden][kGates];                // W_ih_l1 transposed: s_w1[k][row], conflict-free per k
     for (int i = threadIdx.x; i < kGates * kHidden; i += blockDim.x) s_w1[i & 15][i >> 4] = __ldg(hw.wih1 + i);
@@ -173,32 +172,35 @@ head_reduce_independent_kernel(const float *__restrict__ part, int slices, const
     const bool live = b < B;
     const int64_t bb = live ? b : B - 1;                   // dead lanes shadow the last window (shuffles stay full-warp)
     float g4[4];
-    if (flags && flags[bb]) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) g4[q] = gates_listed[bb * kGates + q * kHidden + u];
-    } else {
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+        // lane u of the window's 16 lanes streams gates 4u .. 4u+3 of every slice with one 16-byte load (a window's
+        // row of a slice is one coalesced 256-byte read); every gate is still summed in slice order, so the result is
+        // bit-identical to reduce_gates_kernel.  Afterwards the sums are redistributed: unit u needs gates u, 16+u,
+        // 32+u, 48+u, which sit in lanes (q*16+u)/4 at component (q*16+u)%4 = u%4.
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 *row = reinterpret_cast<const float4 *>(part + bb * kGates) + u;
+        const int64_t slice_stride = B * (kGates / 4);
         int k = 0;
-        for (; k + 8 <= slices; k += 8) {                  // 32 loads in flight per lane; sums stay in slice order
-            float v[8][4];
+        for (; k + 8 <= slices; k += 8) {                  // 8 x 16-byte loads in flight per lane
+            float4 v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float *pk = part + ((int64_t)(k + j) * B + bb) * kGates + u;
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(row + (int64_t)(k + j) * slice_stride);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[j][q] = __ldg(pk + q * kHidden);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) s4[q] += v[j][q];
+            for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
         }
         for (; k < slices; ++k) {
-            const float *pk = part + ((int64_t)k * B + bb) * kGates + u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s4[q] += __ldg(pk + q * kHidden);
+            const float4 v = __ldg(row + (int64_t)k * slice_stride);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
+        const int base16 = lane & 16, comp = u & 3;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) g4[q] = (s4[q] + __ldg(hw.bih0 + q * kHidden + u)) + __ldg(hw.bhh0 + q * kHidden + u);
+        for (int q = 0; q < 4; ++q) {
+            const int src = base16 + ((q * kHidden + u) >> 2);
+            const float a = __shfl_sync(0xffffffffu, s.x, src), b2 = __shfl_sync(0xffffffffu, s.y, src);
+            const float c = __shfl_sync(0xffffffffu, s.z, src), d2 = __shfl_sync(0xffffffffu, s.w, src);
+            const float sum = comp == 0 ? a : comp == 1 ? b2 : comp == 2 ? c : d2;
+            g4[q] = (sum + __ldg(hw.bih0 + q * kHidden + u)) + __ldg(hw.bhh0 + q * kHidden + u);
+        }
     }
     __syncthreads();                                       // s_w1 complete
     // layer 0 from the zero state
@@ -333,11 +335,10 @@ int launch_reduce_gates(const float *partial, int slices, int64_t B, const HeadW
 }
 
 // independent windows: slice reduction + LSTM cells + Linear + age scale in one launch
-int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, const int *flags,
-                            const float *gates_listed, int64_t B, const float *age, int64_t n_age, int apply_sigmoid,
-                            float *out, cudaStream_t st, const char **err) {
-    head_reduce_independent_kernel<<<(unsigned)((B * 16 + 255) / 256), 256, 0, st>>>(partial, slices, flags, gates_listed, hw, age,
-                                                                                  n_age, d.age_coef, apply_sigmoid, out, B);
+int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, int64_t B,
+                            const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err) {
+    head_reduce_independent_kernel<<<(unsigned)((B * 16 + 255) / 256), 256, 0, st>>>(partial, slices, hw, age, n_age, d.age_coef,
+                                                                                  apply_sigmoid, out, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     return 1;

@@ -58,6 +58,12 @@ struct FrontParams {
     int xs_stride, a1_stride;   // padded smem row strides (floats)
     const int *win_list;        // optional: indices of the windows to process (device memory)
     const int *win_count;       //           and how many (device memory)
+    // gate mode (the exact re-computation behind the streaming tensor-core kernels): instead of writing feature
+    // rows, every CTA multiplies the features of its tiles by W_ih_l0^T and writes gate_part[slice][b][64];
+    // slice = blockIdx.x covers tiles [slice * tiles_per_slice, ...), slices >= gate_slices_used are zero-filled
+    float *gate_part;           // [gate_slices][B][64] or nullptr
+    const float *wih0T;         // [L][64]
+    int gate_slices, tiles_per_slice;
     ConvWeights cw;
 };
 
@@ -90,6 +96,11 @@ int launch_frontend_generic_listed(const Dims &d, const ConvWeights &cw, const v
                                    int64_t B, float *feats, int64_t sB, int64_t sP, const int *win_list,
                                    const int *win_count, cudaStream_t st, int num_sms, const char **err);
 
+// exact gate partials of the listed windows straight into the range-partial buffer the head sums (no feature rows)
+int launch_frontend_generic_gates_listed(const Dims &d, const ConvWeights &cw, const void *x, int dtype, int64_t B,
+                                         const float *wih0T, float *gate_part, int gate_slices, const int *win_list,
+                                         const int *win_count, cudaStream_t st, int num_sms, const char **err);
+
 int launch_head(const Dims &d, const HeadWeights &hw, const float *feats, int64_t sB, int64_t sP,
                 int64_t B, const float *age, int64_t n_age, int mode, int apply_sigmoid,
                 float *out, float *gates_ws, float *partial_ws, int ksplit, cudaStream_t st,
@@ -100,9 +111,8 @@ int launch_reduce_gates(const float *partial, int slices, int64_t B, const HeadW
 int launch_lstm_head(const Dims &d, const HeadWeights &hw, const float *gates, int64_t B, const float *age,
                      int64_t n_age, int mode, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
 
-int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, const int *flags,
-                            const float *gates_listed, int64_t B, const float *age, int64_t n_age, int apply_sigmoid,
-                            float *out, cudaStream_t st, const char **err);
+int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, int64_t B,
+                            const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
 
 int choose_ksplit(int64_t B, int L, int num_sms);
 

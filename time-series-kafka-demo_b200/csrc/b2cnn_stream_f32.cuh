@@ -330,7 +330,8 @@ stream_f32_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     *reinterpret_cast<uint4 *>(dst + half * 32 + k) = make_uint4(G[k], G[k + 1], G[k + 2], G[k + 3]);
             }
         }
-        if (row_ok && (nan_probe.x != nan_probe.x || nan_probe.y != nan_probe.y)) p.nanflag[b] = 1;
+        if (row_ok && (nan_probe.x != nan_probe.x || nan_probe.y != nan_probe.y) && atomicExch(&p.nanflag[b], 1) == 0)
+            p.list[atomicAdd(p.count, 1)] = b;
     }
 
     tc_fence_before();

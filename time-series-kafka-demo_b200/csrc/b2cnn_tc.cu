@@ -570,17 +570,19 @@ static int make_tmap(const Dims &d, const void *x, int64_t pitch, int64_t B, CUt
 int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err,
                    bool reduce_here, int *slices_out) {
-    int *flags = reinterpret_cast<int *>(ws);
-    int *list = flags + B, *count = list + B;
-    if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+    (void)feats;
+    // scratch ints: count | flags [B] | list [B]  (count and flags are zeroed by ONE memset; the list needs none)
+    int *count = reinterpret_cast<int *>(ws);
+    int *flags = count + 16, *list = flags + B;
+    if (cudaMemsetAsync(count, 0, sizeof(int) * (B + 16), st) != cudaSuccess) { *err = "memset flags"; return -1; }
     int staged = 0;
     int64_t pitch = d.W;
-    const void *xin = tc_stage_input(d, x, B, reinterpret_cast<char *>(flags) + flags_bytes(B), &pitch, &staged, st);
+    const void *xin = tc_stage_input(d, x, B, reinterpret_cast<char *>(ws) + flags_bytes(B), &pitch, &staged, st);
     CUtensorMap tm;
     if (make_tmap(d, xin, pitch, B, &tm, err) != 0) return -1;
     TcFusedParams p;
     memset(&p, 0, sizeof p);
-    p.partial = partial; p.nanflag = flags;
+    p.partial = partial; p.nanflag = flags; p.list = list; p.count = count;
     p.wpack = reinterpret_cast<const uint8_t *>(s.d_wpack);
     p.B = (int)B; p.W = d.W; p.L = d.L;
     p.tiles_per_cta = s.tiles_per_cta; p.feats_per_cta = s.feats_per_cta; p.chunks_per_cta = s.chunks_per_cta;
@@ -620,22 +622,16 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     int launches = 1 + staged;
-    tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
-    ++launches;
-    // reduce_here == false: the caller's head kernel sums the range partials itself (independent windows) and only
-    // takes gates[b] for flagged windows, which the two launches below recompute exactly
     if (slices_out) *slices_out = s.n_ranges;
-    int n = reduce_here ? launch_reduce_gates(partial, s.n_ranges, B, hw, gates, st, err) : 0;
+    // the exception path: exact gate partials of the flagged windows, written over their rows of `partial`
+    // (one launch; the list was compacted by the kernel itself, an empty list costs one almost-empty launch)
+    int n = launch_frontend_generic_gates_listed(d, cw, x, B2CNN_DTYPE_BF16, B, hw.wih0T, partial, s.n_ranges, list, count, st, num_sms, err);
     if (n < 0) return -1;
     launches += n;
-    // the exception path: exact features + projection for flagged windows only
-    n = launch_frontend_generic_listed(d, cw, x, B2CNN_DTYPE_BF16, B, feats, d.L, 1, list, count, st, num_sms, err);
+    // reduce_here == false: the caller's head kernel sums the range partials itself (independent windows)
+    n = reduce_here ? launch_reduce_gates(partial, s.n_ranges, B, hw, gates, st, err) : 0;
     if (n < 0) return -1;
-    launches += n;
-    proj_listed_kernel<<<64, 256, 0, st>>>(feats, d.L, 1, hw.wih0T, hw.bih0, hw.bhh0, gates, d.L, list, count);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
-    return launches + 1;
+    return launches + n;
 }
 
 bool tc_stream_supported(const TcState &s, const Dims &d, int dtype) {
@@ -646,9 +642,10 @@ bool tc_stream_supported(const TcState &s, const Dims &d, int dtype) {
 int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int64_t B,
                     float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err,
                     bool reduce_here, int *slices_out) {
-    int *flags = reinterpret_cast<int *>(ws);
-    int *list = flags + B, *count = list + B;
-    if (cudaMemsetAsync(flags, 0, sizeof(int) * (2 * B + 1), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+    (void)feats;
+    int *count = reinterpret_cast<int *>(ws);
+    int *flags = count + 16, *list = flags + B;
+    if (cudaMemsetAsync(count, 0, sizeof(int) * (B + 16), st) != cudaSuccess) { *err = "memset flags"; return -1; }
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
     CUtensorMap tm;
     {
@@ -664,7 +661,7 @@ int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const Head
     StreamF32Params pp;
     memset(&pp, 0, sizeof pp);
     TcFusedParams &p = pp.f;
-    p.partial = partial; p.nanflag = flags;
+    p.partial = partial; p.nanflag = flags; p.list = list; p.count = count;
     p.wpack = reinterpret_cast<const uint8_t *>(s.d_wpack_s);
     p.B = (int)B; p.W = d.W; p.L = d.L;
     p.tiles_per_cta = s.tiles_per_cta_s; p.feats_per_cta = s.feats_per_cta_s; p.chunks_per_cta = s.chunks_per_cta_s;
@@ -698,19 +695,13 @@ int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const Head
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     int launches = 1;
-    tc_compact_flags_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(flags, (int)B, list, count);
-    ++launches;
     if (slices_out) *slices_out = s.n_ranges_s;
-    int n = reduce_here ? launch_reduce_gates(partial, s.n_ranges_s, B, hw, gates, st, err) : 0;
+    int n = launch_frontend_generic_gates_listed(d, cw, x, B2CNN_DTYPE_F32, B, hw.wih0T, partial, s.n_ranges_s, list, count, st, num_sms, err);
     if (n < 0) return -1;
     launches += n;
-    n = launch_frontend_generic_listed(d, cw, x, B2CNN_DTYPE_F32, B, feats, d.L, 1, list, count, st, num_sms, err);
+    n = reduce_here ? launch_reduce_gates(partial, s.n_ranges_s, B, hw, gates, st, err) : 0;
     if (n < 0) return -1;
-    launches += n;
-    proj_listed_kernel<<<64, 256, 0, st>>>(feats, d.L, 1, hw.wih0T, hw.bih0, hw.bhh0, gates, d.L, list, count);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
-    return launches + 1;
+    return launches + n;
 }
 
 }  // namespace b2cnn

@@ -33,6 +33,17 @@ namespace b2cnn {
 #ifndef B2CNN_ABLATE
 #define B2CNN_ABLATE 0
 #endif
+// experiment switches (scripts/build_variants.sh): who spins and who parks on an mbarrier.  A parked warp
+// (try_wait with a suspend-time hint -> NANOSLEEP.SYNCS) costs no issue slots but wakes up late.
+#ifndef B2CNN_MMA_SPIN
+#define B2CNN_MMA_SPIN 0                          // MMA issuers: 1 = spin on the accumulator-ring / smem-stage barriers
+#endif
+#ifndef B2CNN_EPI_SPIN
+#define B2CNN_EPI_SPIN 0                          // epilogue: 1 = spin on the accumulator-ring barrier
+#endif
+#ifndef B2CNN_UNROLL8
+#define B2CNN_UNROLL8 1                           // epilogue main loop unrolled over one 8-step projection chunk (compile-time indices)
+#endif
 constexpr int kFuThreads = 384;
 constexpr int kFuWChunkBytes = 3 * 64 * 16 * 2;   // 3 pieces x (64 gates x 16 positions) bf16
 #ifndef B2CNN_COLLECTOR
@@ -48,6 +59,7 @@ constexpr uint32_t kIdescProj = make_idesc_bf16(128, 64);
 struct TcFusedParams {
     float *partial;           // [n_ranges][B][64]
     int *nanflag;             // [B]
+    int *list, *count;        // flagged windows, compacted by the kernel itself: list[atomicAdd(count, 1)] = b (first flagger only)
     const uint8_t *bmats;     // conv1 band matrices [C][SPLITS][1 KB]
     const uint8_t *wpack;     // [n_ranges][chunks_per_cta][kFuWChunkBytes]
     int B, W, L;
@@ -173,8 +185,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         for (int j = 0; j < J; ++j) {
             const int s = i & 1, slot = j & 3;
             if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done); ++m_done; }
+#if B2CNN_MMA_SPIN
+            if (n == 0) mbar_wait(BAR(o + FuBars::kFull + s), (i >> 1) & 1);
+            mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
+#else
             if (n == 0) mbar_wait_parked(BAR(o + FuBars::kFull + s), (i >> 1) & 1);
             mbar_wait_parked(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
+#endif
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t d = tcol + slot * 32;
@@ -231,7 +248,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const bool row_ok = b < p.B;
         // a1 history: abuf[jj & 1] holds the 4 activations x 4 channels produced by stage A of block jj
         // all per-channel state is held as float2 over channel pairs (0,1) and (2,3)
-        float2 pm6[2], pm7[2], abuf[2][4][2], nan_probe = make_float2(0.f, 0.f);
+        float2 pm6[2], pm7[2], abuf[2][4][2];
         float c2c = 0.f;
 #pragma unroll
         for (int q2 = 0; q2 < 2; ++q2) {
@@ -252,22 +269,34 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 5; ++k) w2r[q2][k] = p.w2p[q2][k];
 
-        auto iteration = [&](int jj, auto doA_, auto doB_, auto par_) {
+        // KK >= 0: the step's index inside its 8-step projection chunk is a compile-time constant (the main loop is
+        // unrolled over one chunk): accumulator-ring slots, barrier addresses and parities, the A-operand column and
+        // the chunk-boundary branches all fold, which removes about a third of the loop's instructions (they were
+        // uniform-datapath address / parity arithmetic and branches, not math).  KK == -1: the same step with
+        // everything computed at run time (prologue, the tail after the last whole chunk).
+        auto iteration = [&](int jj, int m, auto doA_, auto doB_, auto par_, auto kk_) {
             constexpr bool doA = decltype(doA_)::value, doB = decltype(doB_)::value;
             constexpr int PAR = decltype(par_)::value;      // == jj & 1 (compile-time register naming)
+            constexpr int KK = decltype(kk_)::value;        // == (jj - 1) & 7, or -1
             const int s = ti & 1;
-            const int jb = jj - 1, m = jb >> 3, kk = jb & 7, u = m & 1;
+            const int jb = jj - 1, kk = KK >= 0 ? KK : (jb & 7), u = m & 1;
+            const int slot0 = KK >= 0 ? ((KK + 1) & 3) : (jj & 3);                    // ring slot of block jj
+            const int slot1 = KK >= 0 ? ((KK + 2) & 3) : ((jj + 1) & 3);              // ... and of block jj + 1
+            const int par1 = KK >= 0 ? (((KK + 2) & 7) >> 2) : (((jj + 1) >> 2) & 1);
             // ---------------- top: barriers ----------------
             if constexpr (doA) {
                 tmem_ld32_wait(Dbuf[PAR]);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + (jj & 3)));
-                if (jj + 1 < J) {                           // prefetch the next block's accumulators
-                    const int s1 = (jj + 1) & 3;
-                    mbar_wait_parked(BAR(o_bar + FuBars::kTFull + s1), ((jj + 1) >> 2) & 1);
+                if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + slot0));
+                if (KK >= 0 || jj + 1 < J) {                // prefetch the next block's accumulators
+#if B2CNN_EPI_SPIN
+                    mbar_wait(BAR(o_bar + FuBars::kTFull + slot1), par1);
+#else
+                    mbar_wait_parked(BAR(o_bar + FuBars::kTFull + slot1), par1);
+#endif
                     tc_fence_after();
-                    tmem_ld32_issue(tlane + s1 * 32, Dbuf[PAR ^ 1]);
+                    tmem_ld32_issue(tlane + slot1 * 32, Dbuf[PAR ^ 1]);
                 }
                 if (n == 0) mbar_wait_parked(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1);   // TMA bytes visible for the tap-9 reads
             }
@@ -358,7 +387,6 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 } else {
                     f = tanh_fold2(make_float2(max_nan(c2[0], c2[1]), max_nan(c2[2], c2[3])), make_float2(p.b2s, p.b2s));
                 }
-                nan_probe = fma2(f, make_float2(0.f, 0.f), nan_probe);
                 // three bf16 pieces of (f0, f1) -> column kk of this lane's row of the A operand
                 const uint32_t h = pack_bf16x2(f.x, f.y);
                 const float2 r1 = sub2(f, make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u)));
@@ -388,9 +416,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 }
             }
             if constexpr (doB) {
-                if (kk == 7 || jb == J - 1) {
+                if (kk == 7 || (KK < 0 && jb == J - 1)) {
                     const uint32_t abase = tlane + 128 + u * 24;
-                    for (int z = kk + 1; z < 8; ++z) { tmem_st1(abase + z, 0u); tmem_st1(abase + z + 8, 0u); tmem_st1(abase + z + 16, 0u); }
+                    if (KK < 0)
+                        for (int z = kk + 1; z < 8; ++z) { tmem_st1(abase + z, 0u); tmem_st1(abase + z + 8, 0u); tmem_st1(abase + z + 16, 0u); }
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -402,32 +431,54 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         using F_ = std::integral_constant<bool, false>;
         using P0 = std::integral_constant<int, 0>;
         using P1 = std::integral_constant<int, 1>;
-        iteration(0, T_{}, F_{}, P0{});
+        using KR = std::integral_constant<int, -1>;
+        iteration(0, 0, T_{}, F_{}, P0{}, KR{});
         int jj = 1;
+#if B2CNN_UNROLL8
+        // whole chunks whose every step has a successor block (jj + 1 < J): steps 8c .. 8c+7 with compile-time indices
+        const int nfull = J >= 2 ? (J - 2) >> 3 : 0;
+#pragma unroll 1
+        for (int c = 0; c < nfull; ++c, jj += 8) {
+            iteration(jj + 0, c, T_{}, T_{}, P1{}, std::integral_constant<int, 0>{});
+            iteration(jj + 1, c, T_{}, T_{}, P0{}, std::integral_constant<int, 1>{});
+            iteration(jj + 2, c, T_{}, T_{}, P1{}, std::integral_constant<int, 2>{});
+            iteration(jj + 3, c, T_{}, T_{}, P0{}, std::integral_constant<int, 3>{});
+            iteration(jj + 4, c, T_{}, T_{}, P1{}, std::integral_constant<int, 4>{});
+            iteration(jj + 5, c, T_{}, T_{}, P0{}, std::integral_constant<int, 5>{});
+            iteration(jj + 6, c, T_{}, T_{}, P1{}, std::integral_constant<int, 6>{});
+            iteration(jj + 7, c, T_{}, T_{}, P0{}, std::integral_constant<int, 7>{});
+        }
+#endif
 #pragma unroll 1
         for (; jj + 1 < J; jj += 2) {                       // two steps per trip: register names alternate
-            iteration(jj, T_{}, T_{}, P1{});
-            iteration(jj + 1, T_{}, T_{}, P0{});
+            iteration(jj, (jj - 1) >> 3, T_{}, T_{}, P1{}, KR{});
+            iteration(jj + 1, jj >> 3, T_{}, T_{}, P0{}, KR{});
         }
-        if (jj < J) { iteration(jj, T_{}, T_{}, P1{}); ++jj; }
-        if (J & 1) iteration(J, F_{}, T_{}, P1{}); else iteration(J, F_{}, T_{}, P0{});
+        if (jj < J) { iteration(jj, (jj - 1) >> 3, T_{}, T_{}, P1{}, KR{}); ++jj; }
+        if (J & 1) iteration(J, (J - 1) >> 3, F_{}, T_{}, P1{}, KR{}); else iteration(J, (J - 1) >> 3, F_{}, T_{}, P0{}, KR{});
 
         // ---- gate pre-activations of this CTA's position range -> partial[range][window][64]
         mbar_wait_parked(BAR(o_bar + FuBars::kGFull), 0);
         tc_fence_after();
         float *dst = p.partial + ((int64_t)blockIdx.y * p.B + b) * kGates;
+        // A NaN feature (a NaN / inf sample met a zero of the band matrix, or a real NaN) makes every gate it is
+        // multiplied into NaN -- zero weights included -- so the 64 sums themselves are the probe: no per-step test.
+        bool bad = false;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             uint32_t G[32];
             tmem_ld32_issue(tlane + 192 + half * 32, G);
             tmem_ld32_wait(G);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) bad |= (G[k] & 0x7fffffffu) > 0x7f800000u;
             if (row_ok) {
 #pragma unroll
                 for (int k = 0; k < 32; k += 4)
                     *reinterpret_cast<uint4 *>(dst + half * 32 + k) = make_uint4(G[k], G[k + 1], G[k + 2], G[k + 3]);
             }
         }
-        if (row_ok && (nan_probe.x != nan_probe.x || nan_probe.y != nan_probe.y)) p.nanflag[b] = 1;
+        // up to n_ranges CTAs may flag the same window: the first one appends it to the list of the exact re-computation
+        if (row_ok && bad && atomicExch(&p.nanflag[b], 1) == 0) p.list[atomicAdd(p.count, 1)] = b;
     }
 
     tc_fence_before();
@@ -461,26 +512,6 @@ __global__ void tc_pack_wih_kernel(const float *__restrict__ wih, uint8_t *__res
         const __nv_bfloat16 hb = __float2bfloat16_rn(w);
         base[piece * 1024 + off] = __bfloat16_as_ushort(hb);
         w -= __bfloat162float(hb);
-    }
-}
-
-// exact projection for the (rare) windows the tensor-core kernel flagged: one CTA per listed
-// window, gates[b][g] = (sum_p feats[b][p] * WT[p][g] + b_ih[g]) + b_hh[g]
-__global__ void __launch_bounds__(256)
-proj_listed_kernel(const float *__restrict__ feats, int64_t sB, int64_t sP, const float *__restrict__ WT,
-                   const float *__restrict__ bih, const float *__restrict__ bhh, float *__restrict__ gates, int L,
-                   const int *__restrict__ list, const int *__restrict__ count) {
-    __shared__ float red[4][kGates];
-    const int g = threadIdx.x & 63, sl = threadIdx.x >> 6;
-    const int n = *count;
-    for (int wi = blockIdx.x; wi < n; wi += gridDim.x) {
-        const int b = list[wi];
-        float acc = 0.f;
-        for (int pp = sl; pp < L; pp += 4) acc = fmaf(feats[(int64_t)b * sB + (int64_t)pp * sP], WT[(int64_t)pp * kGates + g], acc);
-        red[sl][g] = acc;
-        __syncthreads();
-        if (sl == 0) gates[(int64_t)b * kGates + g] = (((red[0][g] + red[1][g]) + (red[2][g] + red[3][g])) + bih[g]) + bhh[g];
-        __syncthreads();
     }
 }
 

@@ -201,6 +201,7 @@ class B200MyCNN(nn.Module):
     def set_path(self, path: str):
         """'auto' | 'generic' (exact fp32 CUDA cores) | 'tensorcore' (tcgen05 conv1)."""
         self._path = path
+        self.__dict__["_ws_need"] = {}                     # the scratch size depends on the path a call takes
         if self._handle is not None:
             capi.check(capi.load_library().b2cnn_set_option(self._handle, b"path", _PATHS[path]), "b2cnn_set_option")
 
@@ -209,6 +210,7 @@ class B200MyCNN(nn.Module):
         end and the projection as separate kernels."""
         lib, h = self._ensure_handle()
         capi.check(lib.b2cnn_set_option(h, key.encode(), int(value)), "b2cnn_set_option")
+        self.__dict__["_ws_need"] = {}
 
     def set_profile(self, on: bool = True):
         """Record CUDA events around the stages of every forward (bench.py's roofline figure)."""
@@ -229,11 +231,11 @@ class B200MyCNN(nn.Module):
             return "none"
         return _PATH_NAMES.get(int(capi.load_library().b2cnn_last_path(self._handle)), "none")
 
-    def _workspace(self, lib, h, B: int, mode: int, dev) -> torch.Tensor:
+    def _workspace(self, lib, h, B: int, mode: int, dtype: int, dev) -> torch.Tensor:
         cache = self.__dict__.setdefault("_ws_need", {})
-        need = cache.get((B, mode))
+        need = cache.get((B, mode, dtype))
         if need is None:
-            need = cache[(B, mode)] = int(lib.b2cnn_workspace_bytes(h, B, mode))
+            need = cache[(B, mode, dtype)] = int(lib.b2cnn_workspace_bytes_for(h, B, mode, dtype))
         ws = self._ws
         if ws is None or ws.numel() < need or ws.device != dev:
             ws = self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -271,7 +273,7 @@ class B200MyCNN(nn.Module):
         if age.device != dev:
             age = age.to(dev)
         out = torch.empty(B, dtype=torch.float32, device=dev)
-        ws = self._workspace(lib, h, B, mode, dev)
+        ws = self._workspace(lib, h, B, mode, dtype, dev)
         if torch.cuda.current_device() == dev.index:            # the usual case: no device switch needed
             rc = lib.b2cnn_forward(h, x.data_ptr(), dtype, B, age.data_ptr(), n_age, mode, int(sigmoid),
                                    out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)

@@ -100,6 +100,9 @@ def assemble_windows_gpu(record: NumericsRecord, device="cuda", dtype=None):
     ws_bytes = lib.b2cnn_prep_workspace_bytes(n, float(record.fs), len(sel), ctypes.byref(cfg))
     if n_win < 0 or ws_bytes < 0:
         raise RuntimeError(f"b2cnn_prep: {capi.last_error()}")
+    if n_win == 0 or len(sel) == 0:                                # record shorter than one 600 s window / nothing selected
+        return (torch.zeros((n_win if len(sel) == 0 else 0, N_CHANNELS, WINDOW_POINTS), dtype=dtype, device=dev),
+                torch.arange(n_win if len(sel) == 0 else 0, dtype=torch.float64, device=dev) * float(STRIDE_S))
     with torch.cuda.device(dev):
         raw_d = torch.from_numpy(raw_h).to(dev)
         x = torch.empty((n_win, N_CHANNELS, WINDOW_POINTS), dtype=dtype, device=dev)
