@@ -99,6 +99,14 @@ int b2cnn_forward(b2cnn_handle *h, const void *x, int dtype, int64_t B, const fl
                   int64_t n_age, int mode, int apply_sigmoid, float *out, void *workspace,
                   int64_t workspace_bytes, void *stream);
 
+/* b2cnn_forward for windows whose channel rows are `x_pitch` ELEMENTS apart (x_pitch >= W; window b starts at
+ * x + b * C * x_pitch): a producer that pads its rows to a multiple of 16 bytes (8 bf16 / 4 fp32 samples) lets TMA
+ * stream windows of ANY length straight from `x`; a contiguous tensor with W % 8 != 0 (7500, 37500 ...) has to be
+ * re-pitched into scratch first (one extra read + write of the input).  The pad is never read. */
+int b2cnn_forward_pitched(b2cnn_handle *h, const void *x, int dtype, int64_t B, int64_t x_pitch, const float *age,
+                          int64_t n_age, int mode, int apply_sigmoid, float *out, void *workspace,
+                          int64_t workspace_bytes, void *stream);
+
 /* Same call with HOST pointers (ideally pinned): chunked H2D copy of x overlapped with
  * compute, D2H of the B results; synchronous on return.  Uses library-owned staging. */
 int b2cnn_forward_host(b2cnn_handle *h, const void *x_host, int dtype, int64_t B,

@@ -283,3 +283,37 @@ def test_single_launch_small_window_kernel(golden5):
     want = torch.sigmoid(O.ref_independent(ref, xb.float(), ages)).numpy()
     got = m3.predict(xb.to(DEV), ages.to(DEV), return_prob=True).cpu().numpy()
     assert m3.gpu_launches == 1 and rel_err(got, want) <= TOL
+
+
+# ------------------------------------------------------------------ production shape, batched: [P, 10, 120]
+@pytest.mark.parametrize("n,P,dtype", [(5, 1000, torch.float32), (5, 37, torch.float32), (5, 4096, torch.bfloat16),
+                                       (4, 600, torch.float32), (3, 300, torch.float32), (2, 9, torch.float32)])
+def test_short_window_batch_kernel_production_shape(n, P, dtype):
+    """All patients of a trigger in ONE launch (one warp per window): the shipped checkpoints MyCNN5 (10 ch, k1=10,
+    pool(3,2)), MyCNN4 (10 ch, k1=5, pool(2,2)), MyCNN2/3 (7 ch) on [P, C, 120] -- vs the oracle's per-window loop
+    and vs the per-window launch path."""
+    g, sd = load_golden("mycnn5_xtestinput.npz" if n == 5 else f"mycnn{n}_ckpt.npz")
+    m = tskd_b200.B200MyCNN.from_reference(sd, age_coef=1e-8).to(DEV)
+    C = m.arch.in_channels
+    x = tskd_b200.synth.make_windows(P, C, 120, "physio", seed=20 + n, dtype=dtype, device=DEV)
+    x[1] = tskd_b200.synth.make_windows(1, C, 120, "normal", seed=5, dtype=dtype, device=DEV)[0]
+    ages = tskd_b200.synth.make_ages(P, seed=20 + n, device=DEV)
+    y = m.predict(x, ages)
+    assert m.gpu_launches == 1 and m.last_path == "generic"
+    oarch = replace(O.ARCH_MYCNN5 if n == 5 else O.ARCHS["mycnn3"], in_channels=C, age_coef=1e-8, has_out12=("out1.weight" in sd))
+    ref = O.RefMyCNN(oarch); ref.load_state_dict(sd); ref.eval()
+    k = min(P, 256)
+    want = O.ref_independent(ref, x[:k].float().cpu(), ages[:k].cpu()).numpy()
+    assert rel_err_elem(y[:k].cpu().numpy(), want) <= TOL
+    # the same windows one launch each (B < 8 takes the single-window kernel): same numbers to fp32 noise
+    one = torch.cat([m.predict(x[i:i + 1], ages[i:i + 1]) for i in range(0, k, max(1, k // 16))])
+    assert rel_err(one.cpu().numpy(), y[:k:max(1, k // 16)].cpu().numpy()) <= 2e-6
+    prob = m.predict(x[:k], ages[:k], return_prob=True).cpu().numpy()
+    assert rel_err(prob, 1 / (1 + np.exp(-want.astype(np.float64)))) <= TOL
+    # NaN / inf semantics of the reference (max_pool1d propagates NaN, tanh saturates inf)
+    xe = x[:16].clone().float()
+    xe[3, 2, 50] = float("nan"); xe[5, 0, 119] = float("inf"); xe[7, C - 1, 0] = float("-inf")
+    we = O.ref_independent(ref, xe.cpu(), ages[:16].cpu()).numpy()
+    ge = m.predict(xe, ages[:16]).cpu().numpy()
+    assert np.array_equal(np.isnan(we), np.isnan(ge)) and np.isnan(we[3]) and np.isfinite(we[5])
+    assert rel_err(ge[~np.isnan(we)], we[~np.isnan(we)]) <= TOL

@@ -215,3 +215,36 @@ def test_f32_falls_back_to_generic_when_rows_are_not_16_byte_multiples():
     y = m.predict(x.to(DEV), ages.to(DEV))
     assert m.last_path == "generic"
     assert rel_err(y.cpu().numpy(), O.ref_independent(ref, x, ages).numpy()) <= TOL
+
+
+@pytest.mark.parametrize("kind,C,W,B,dtype,path", [
+    ("mycnn5", 3, 7500, 150, torch.bfloat16, "tensorcore"),     # W % 8 == 4: TMA straight from the padded rows, no re-pitching copy
+    ("mycnn5", 3, 37500, 12, torch.bfloat16, "tensorcore"),
+    ("mycnn3", 3, 7500, 130, torch.bfloat16, "tensorcore"),
+    ("mycnn5", 2, 1533, 300, torch.bfloat16, "tensorcore"),     # odd W
+    ("mycnn5", 3, 7501, 70, torch.float32, "stream"),           # fp32: W % 4 != 0 is generic when contiguous, streamed when padded
+    ("mycnn5", 3, 7500, 33, torch.float32, "generic"),          # the generic kernels honour the pitch too
+    ("mycnn3", 3, 1502, 40, torch.bfloat16, "generic"),         # ... and the single-launch small-window kernel
+])
+def test_row_padded_windows_need_no_staging_copy(kind, C, W, B, dtype, path):
+    """b2cnn_forward_pitched: a producer that pads its rows to 16 bytes (B200MyCNN.empty_windows) gets the same logits as
+    the contiguous tensor -- bit for bit on the tensor-core paths, where the only difference is the skipped staging copy."""
+    ref, m = _pair(C, W, path="auto", kind=kind)
+    x = tskd_b200.synth.make_windows(B, C, W, "normal", seed=11, dtype=dtype, device=DEV)
+    ages = tskd_b200.synth.make_ages(B, seed=11, device=DEV)
+    if path == "generic":
+        m.set_path("generic")
+    y_c = m.predict(x, ages)
+    launches_c, path_c = m.gpu_launches, m.last_path
+    xp = m.empty_windows(B, dtype=dtype)
+    assert not xp.is_contiguous() and xp.stride(1) % (16 // xp.element_size()) == 0 and xp.shape == x.shape
+    xp.copy_(x)
+    y_p = m.predict(xp, ages)
+    assert m.last_path == path, (m.last_path, path_c)
+    want = O.ref_independent(ref, x.float().cpu(), ages.cpu()).numpy()
+    assert rel_err(y_p.cpu().numpy(), want) <= TOL
+    if path == "tensorcore":
+        assert torch.equal(y_p, y_c)
+        assert m.gpu_launches == launches_c - 1 and m.gpu_launches <= 3         # fused + exact-recompute (empty) + head
+    y_s = m.predict(xp[3:9], ages[3:9])                                          # a slice keeps the pitch
+    assert rel_err(y_s.cpu().numpy(), want[3:9]) <= TOL

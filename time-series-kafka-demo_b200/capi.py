@@ -22,7 +22,7 @@ SAMPLES_ADC16, SAMPLES_F64 = 0, 1
 
 # every symbol include/b2cnn.h declares (tests/test_host.py::test_library_exports_every_declared_symbol checks the list)
 SYMBOLS = ("b2cnn_l_out", "b2cnn_weight_count", "b2cnn_create", "b2cnn_destroy",
-           "b2cnn_set_weights", "b2cnn_workspace_bytes", "b2cnn_workspace_bytes_for", "b2cnn_forward", "b2cnn_forward_host",
+           "b2cnn_set_weights", "b2cnn_workspace_bytes", "b2cnn_workspace_bytes_for", "b2cnn_forward", "b2cnn_forward_pitched", "b2cnn_forward_host",
            "b2cnn_features", "b2cnn_set_option", "b2cnn_get_option", "b2cnn_last_launch_count",
            "b2cnn_last_path", "b2cnn_last_stage_ms", "b2cnn_last_error", "b2cnn_version",
            "b2cnn_prep_window_count", "b2cnn_prep_workspace_bytes", "b2cnn_prep_windows",
@@ -73,6 +73,8 @@ def load_library() -> ctypes.CDLL:
     lib.b2cnn_workspace_bytes_for.argtypes = [c_vp, c_i64, c_int, c_int]; lib.b2cnn_workspace_bytes_for.restype = c_i64
     lib.b2cnn_forward.argtypes = [c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_vp]
     lib.b2cnn_forward.restype = c_int
+    lib.b2cnn_forward_pitched.argtypes = [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_vp]
+    lib.b2cnn_forward_pitched.restype = c_int
     lib.b2cnn_forward_host.argtypes = [c_vp, c_vp, c_int, c_i64, c_vp, c_i64, c_int, c_int, c_vp]
     lib.b2cnn_forward_host.restype = c_int
     lib.b2cnn_features.argtypes = [c_vp, c_vp, c_int, c_i64, c_vp, c_vp]; lib.b2cnn_features.restype = c_int

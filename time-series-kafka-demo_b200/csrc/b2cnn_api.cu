@@ -82,7 +82,7 @@ static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 static bool derive_dims(const b2cnn_config &c, Dims &d) {
     d.C = c.in_channels; d.K1 = c.k1; d.K2 = c.k2; d.PK = c.pool_k; d.PS = c.pool_s; d.W = c.window;
-    d.act = c.act; d.has_affine = (c.flags & B2CNN_FLAG_AFFINE) ? 1 : 0; d.age_coef = c.age_coef;
+    d.act = c.act; d.has_affine = (c.flags & B2CNN_FLAG_AFFINE) ? 1 : 0; d.age_coef = c.age_coef; d.XP = c.window;
     if (d.C < 1 || d.K1 < 1 || d.K2 < 1 || d.PK < 1 || d.PS < 1 || d.W < 1) return false;
     d.L1 = d.W - d.K1 + 1;
     if (d.L1 < d.PK) return false;
@@ -338,9 +338,11 @@ static bool use_tc(b2cnn_handle *h, int dtype, int64_t B, int mode) {
     return tc_supported(h->tc, h->d, dtype, B, mode);
 }
 
-static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, const float *age, int64_t n_age,
+static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, int64_t xpitch, const float *age, int64_t n_age,
                           int mode, int apply_sigmoid, float *out, void *ws, int64_t ws_bytes, cudaStream_t st) {
-    const Dims &d = h->d;
+    Dims d = h->d;
+    if (xpitch < d.W || xpitch > 0x7fffffff) return fail(B2CNN_EINVAL, "b2cnn_forward: x_pitch must be >= window");
+    d.XP = (int)xpitch;
     const int ks = choose_ksplit(B, d.L, h->num_sms);
     const WsLayout wl = ws_layout(h, B, mode, dtype);
     if (ws_bytes < wl.total) return fail(B2CNN_ESTATE, "b2cnn_forward: workspace smaller than b2cnn_workspace_bytes_for()");
@@ -353,6 +355,11 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
     int launches = 0;
     const bool tc = use_tc(h, dtype, B, mode);
     const bool stream = h->opt_path != B2CNN_PATH_GENERIC && h->opt_stream && tc_stream_supported(h->tc, d, dtype);
+    if (!wl.feats && !stream && !(tc && tc_fused_supported(h->tc, d, dtype)) &&
+        !(h->opt_path != B2CNN_PATH_TENSORCORE && h->opt_small && (mode == B2CNN_MODE_INDEPENDENT || B == 1) && B <= 256 &&
+          (int64_t)d.C * d.W <= 8192 && small_supported(d)) &&
+        !(h->opt_path != B2CNN_PATH_TENSORCORE && h->opt_small && mode == B2CNN_MODE_INDEPENDENT && B >= 8 && batch_supported(d)))
+        return fail(B2CNN_ESTATE, "b2cnn_forward: this x_pitch takes a path that needs feature rows; size the workspace with b2cnn_workspace_bytes()");
     if (!tc && !stream && h->opt_path == B2CNN_PATH_TENSORCORE)
         return fail(B2CNN_EARCH, "path=tensorcore requested but this shape/dtype/mode is not supported by the tcgen05 kernel");
     const bool prof = h->opt_profile != 0;
@@ -360,6 +367,14 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
         for (int i = 0; i < 3; ++i)
             if (!h->ev_stage[i]) CU_TRY(cudaEventCreate(&h->ev_stage[i]));
         CU_TRY(cudaEventRecord(h->ev_stage[0], st));
+    }
+    // short windows, many of them (all patients of a trigger, [P,10,120]): one launch, one warp per window
+    if (h->opt_path != B2CNN_PATH_TENSORCORE && h->opt_small && mode == B2CNN_MODE_INDEPENDENT && B >= 8 && batch_supported(d)) {
+        int n1 = launch_short_batch(d, h->cw, h->hw, x, dtype, B, age, n_age, apply_sigmoid, out, h->num_sms, st, &err);
+        if (n1 < 0) return fail(B2CNN_ECUDA, std::string("short-window batch kernel: ") + err);
+        if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[1], st)); CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }
+        h->last_launches = n1; h->last_path = B2CNN_PATH_GENERIC;
+        return B2CNN_OK;
     }
     // short windows, few of them (the production call is [1,10,120]): one launch does everything
     if (h->opt_path != B2CNN_PATH_TENSORCORE && h->opt_small && (mode == B2CNN_MODE_INDEPENDENT || B == 1) && B <= 256 &&
@@ -441,7 +456,18 @@ extern "C" int b2cnn_forward(b2cnn_handle *h, const void *x, int dtype, int64_t 
     if (!workspace || workspace_bytes < ws_layout(h, B, mode, dtype).total)
         return fail(B2CNN_ESTATE, "b2cnn_forward: workspace missing or smaller than b2cnn_workspace_bytes_for()");
     DEVICE_GUARD(h->device);
-    return forward_device(h, x, dtype, B, age, n_age, mode, apply_sigmoid, out, workspace, workspace_bytes, (cudaStream_t)stream);
+    return forward_device(h, x, dtype, B, h->d.W, age, n_age, mode, apply_sigmoid, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int b2cnn_forward_pitched(b2cnn_handle *h, const void *x, int dtype, int64_t B, int64_t x_pitch, const float *age,
+                                     int64_t n_age, int mode, int apply_sigmoid, float *out, void *workspace,
+                                     int64_t workspace_bytes, void *stream) {
+    int rc = check_call(h, x, dtype, B, age, n_age, mode, out);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < ws_layout(h, B, mode, dtype).total)
+        return fail(B2CNN_ESTATE, "b2cnn_forward_pitched: workspace missing or smaller than b2cnn_workspace_bytes_for()");
+    DEVICE_GUARD(h->device);
+    return forward_device(h, x, dtype, B, x_pitch, age, n_age, mode, apply_sigmoid, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int b2cnn_features(b2cnn_handle *h, const void *x, int dtype, int64_t B, float *feats, void *stream) {
@@ -521,7 +547,7 @@ extern "C" int b2cnn_forward_host(b2cnn_handle *h, const void *x_host, int dtype
                                cudaMemcpyHostToDevice, h->s_copy));
         CU_TRY(cudaEventRecord(h->ev_copied[s], h->s_copy));
         CU_TRY(cudaStreamWaitEvent(h->s_comp, h->ev_copied[s], 0));
-        rc = forward_device(h, h->st_x[s], dtype, nb, n_age == 1 ? h->st_age : h->st_age + b0, n_age == 1 ? 1 : nb, mode,
+        rc = forward_device(h, h->st_x[s], dtype, nb, d.W, n_age == 1 ? h->st_age : h->st_age + b0, n_age == 1 ? 1 : nb, mode,
                             apply_sigmoid, h->st_out + b0, h->st_ws, ws_bytes, h->s_comp);
         if (rc) return rc;
         launches += h->last_launches;

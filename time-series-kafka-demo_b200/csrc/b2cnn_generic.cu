@@ -49,7 +49,6 @@ __global__ void __launch_bounds__(256, 2) frontend_kernel(const __grid_constant_
     constexpr int NQ = PS + PK;                // conv2 outputs for two final positions
     constexpr int NA = NQ + K2 - 1;
     const int tid = threadIdx.x;
-    const int W = p.d.W;
     const int act = p.d.act, aff = p.d.has_affine;
     const bool gate_mode = p.gate_part != nullptr;
     __shared__ float gred[4][kGates];
@@ -71,9 +70,9 @@ __global__ void __launch_bounds__(256, 2) frontend_kernel(const __grid_constant_
         const int n_runs = (nj + RUN - 1) / RUN;
         const int n_runs2 = (tp + 1) / 2;
         // ---- stage 1: input tile -> smem (fp32) ------------------------------------------
-        const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * W + i0;
+        const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * p.d.XP + i0;
         for (int c = 0; c < C; ++c) {
-            const Tin *row = xb + (int64_t)c * W;
+            const Tin *row = xb + (int64_t)c * p.d.XP;
             float *dst = xs + c * p.xs_stride;
             for (int i = tid; i < ni; i += 256) dst[padi(i)] = ld_in<Tin>(row + i);
         }
@@ -198,7 +197,7 @@ template <typename Tin>
 __global__ void __launch_bounds__(256) frontend_any_kernel(const __grid_constant__ FrontParams p) {
     extern __shared__ float smem[];
     const Dims &d = p.d;
-    const int C = d.C, K1 = d.K1, K2 = d.K2, PK = d.PK, PS = d.PS, W = d.W;
+    const int C = d.C, K1 = d.K1, K2 = d.K2, PK = d.PK, PS = d.PS;
     float *xs = smem;
     float *a1 = smem + C * p.xs_stride;
     const int tid = threadIdx.x;
@@ -212,9 +211,9 @@ __global__ void __launch_bounds__(256) frontend_any_kernel(const __grid_constant
     const int nwin = p.win_count ? *p.win_count : p.B;
     for (int wi = blockIdx.y; wi < nwin; wi += gridDim.y) {
         const int b = p.win_list ? p.win_list[wi] : wi;
-        const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * W + i0;
+        const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * d.XP + i0;
         for (int c = 0; c < C; ++c)
-            for (int i = tid; i < ni; i += 256) xs[c * p.xs_stride + padi(i)] = ld_in<Tin>(xb + (int64_t)c * W + i);
+            for (int i = tid; i < ni; i += 256) xs[c * p.xs_stride + padi(i)] = ld_in<Tin>(xb + (int64_t)c * d.XP + i);
         __syncthreads();
         for (int e = tid; e < nj * kCMid; e += 256) {
             const int j = e >> 2, o = e & 3;

@@ -25,6 +25,8 @@ struct Dims {
     int L1, P1, L2, L;       // conv1 out, pool1 out, conv2 out, pool2 out (= LSTM input size)
     int act, has_affine;
     float age_coef;
+    int XP;                  // row pitch of x in elements (>= W): channel rows start XP apart, windows C*XP apart.
+                             // == W for a contiguous [B][C][W] tensor; set per call (b2cnn_forward_pitched)
 };
 
 // Conv weights travel as a by-value kernel parameter: they land in the constant bank, so the
@@ -120,6 +122,11 @@ int choose_ksplit(int64_t B, int L, int num_sms);
 bool small_supported(const Dims &d);
 int launch_small_forward(const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int dtype, int64_t B,
                          const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
+
+// b2cnn_batch.cu: many short windows per launch, one warp per window (the production shape [P, 10, 120])
+bool batch_supported(const Dims &d);
+int launch_short_batch(const Dims &d, const ConvWeights &cw, const HeadWeights &hw, const void *x, int dtype, int64_t B,
+                       const float *age, int64_t n_age, int apply_sigmoid, float *out, int num_sms, cudaStream_t st, const char **err);
 
 // b2cnn_prep.cu: preprocessing + window assembly in front of the model call (f2 + f1)
 int64_t prep_window_count(int64_t n_samples, double fs, const b2cnn_prep_config *cfg);

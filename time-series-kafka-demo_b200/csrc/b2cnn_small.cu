@@ -45,8 +45,13 @@ __global__ void __launch_bounds__(256) small_forward_kernel(const __grid_constan
     float *h = g + kGates;              // [16]
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
-    const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * W;
-    for (int i = tid; i < C * W; i += 256) xs[i] = ld_small<Tin>(xb + i);
+    const Tin *xb = reinterpret_cast<const Tin *>(p.x) + (int64_t)b * C * d.XP;
+    if (d.XP == W) {
+        for (int i = tid; i < C * W; i += 256) xs[i] = ld_small<Tin>(xb + i);
+    } else {
+        for (int c = 0; c < C; ++c)
+            for (int i = tid; i < W; i += 256) xs[c * W + i] = ld_small<Tin>(xb + (int64_t)c * d.XP + i);
+    }
     __syncthreads();
     // conv1 + act + pool (models.py:23-24); activation before pooling exactly as written
     for (int e = tid; e < P1 * kCMid; e += 256) {

@@ -412,17 +412,22 @@ int64_t tc_workspace_bytes(const TcState &s, const Dims &d, int64_t B) {
     return flags_bytes(B) + xpad_bytes(d, B);
 }
 
+// rows of W samples, `sp` elements apart -> rows Wp (multiple of 8) apart, tail zero-filled.
+// VEC 8: W % 4 == 0 and sp % 4 == 0: every row starts 8-byte aligned; one thread moves 16 output bytes with two
+//        8-byte loads (a 16-byte load would be misaligned on every other row) and ONE 16-byte store.
+// VEC 1: any W (2-byte accesses).
 template <int VEC>
-__global__ void tc_repack_rows_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int64_t rows, int W, int Wp) {
+__global__ void tc_repack_rows_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int64_t rows, int W, int64_t sp, int Wp) {
     const int per_row = Wp / VEC;
     for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
-        const uint16_t *in = src + r * W;
+        const uint16_t *in = src + r * sp;
         uint16_t *out = dst + r * Wp;
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
-            if (VEC == 4) {
-                uint2 v = make_uint2(0u, 0u);
-                if (i * 4 < W) v = *reinterpret_cast<const uint2 *>(in + i * 4);     // W % 4 == 0 here
-                *reinterpret_cast<uint2 *>(out + i * 4) = v;
+            if (VEC == 8) {
+                uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+                if (i * 8 < W) a = __ldg(reinterpret_cast<const uint2 *>(in + i * 8));
+                if (i * 8 + 4 < W) b = __ldg(reinterpret_cast<const uint2 *>(in + i * 8 + 4));
+                *reinterpret_cast<uint4 *>(out + i * 8) = make_uint4(a.x, a.y, b.x, b.y);
             } else {
                 out[i] = i < W ? in[i] : (uint16_t)0;
             }
@@ -430,18 +435,19 @@ __global__ void tc_repack_rows_kernel(const uint16_t *__restrict__ src, uint16_t
     }
 }
 
-// returns the pointer / pitch the tensor map must describe (x itself when already aligned)
+// returns the pointer / pitch the tensor map must describe (x itself when its rows are 16-byte aligned: W % 8 == 0
+// for a contiguous tensor, or a producer that padded the row pitch -- b2cnn_forward_pitched)
 static const void *tc_stage_input(const Dims &d, const void *x, int64_t B, void *scratch_after_flags, int64_t *pitch,
                                   int *launches, cudaStream_t st) {
-    *pitch = d.W;
-    if ((d.W % 8) == 0) return x;
+    *pitch = d.XP;
+    if ((d.XP % 8) == 0) return x;
     const int64_t rows = B * d.C;
     const int Wp = (int)padded_w(d);
-    dim3 grid(8, (unsigned)(rows < 16384 ? rows : 16384));
-    if (d.W % 4 == 0)
-        tc_repack_rows_kernel<4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<uint16_t *>(scratch_after_flags), rows, d.W, Wp);
+    dim3 grid(4, (unsigned)(rows < 32768 ? rows : 32768));
+    if (d.W % 4 == 0 && d.XP % 4 == 0)
+        tc_repack_rows_kernel<8><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<uint16_t *>(scratch_after_flags), rows, d.W, d.XP, Wp);
     else
-        tc_repack_rows_kernel<1><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<uint16_t *>(scratch_after_flags), rows, d.W, Wp);
+        tc_repack_rows_kernel<1><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t *>(x), reinterpret_cast<uint16_t *>(scratch_after_flags), rows, d.W, d.XP, Wp);
     *pitch = Wp;
     ++*launches;
     return scratch_after_flags;
@@ -525,7 +531,7 @@ int tc_frontend(TcState &s, const Dims &d, const ConvWeights &cw, const void *x,
         *err = "memset flags";
     } else {
         int staged = 0;
-        int64_t pitch = d.W;
+        int64_t pitch = d.XP;
         const void *xin = tc_stage_input(d, x, B, reinterpret_cast<char *>(flags) + flags_bytes(B), &pitch, &staged, st);
         int n = launch_tc_kernel(s, d, cw, xin, pitch, B, feats, sB, sP, flags, st, err);
         if (n >= 0) {
@@ -576,7 +582,7 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     int *flags = count + 16, *list = flags + B;
     if (cudaMemsetAsync(count, 0, sizeof(int) * (B + 16), st) != cudaSuccess) { *err = "memset flags"; return -1; }
     int staged = 0;
-    int64_t pitch = d.W;
+    int64_t pitch = d.XP;
     const void *xin = tc_stage_input(d, x, B, reinterpret_cast<char *>(ws) + flags_bytes(B), &pitch, &staged, st);
     CUtensorMap tm;
     if (make_tmap(d, xin, pitch, B, &tm, err) != 0) return -1;
@@ -635,7 +641,7 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
 }
 
 bool tc_stream_supported(const TcState &s, const Dims &d, int dtype) {
-    return s.ready && s.stream_ready && dtype == B2CNN_DTYPE_F32 && (arch_ok(d) || arch1_ok(d)) && d.C <= 3 && (d.W % 4) == 0;
+    return s.ready && s.stream_ready && dtype == B2CNN_DTYPE_F32 && (arch_ok(d) || arch1_ok(d)) && d.C <= 3 && (d.XP % 4) == 0;
 }
 
 // fp32 windows: streaming front end + projection -> gates[B][64]; flagged (NaN) windows are recomputed exactly.
@@ -650,7 +656,7 @@ int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const Head
     CUtensorMap tm;
     {
         cuuint64_t gdim[3] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)B};
-        cuuint64_t gstr[2] = {(cuuint64_t)d.W * 4, (cuuint64_t)d.C * d.W * 4};
+        cuuint64_t gstr[2] = {(cuuint64_t)d.XP * 4, (cuuint64_t)d.C * d.XP * 4};
         cuuint32_t box[3] = {32, 1, kTcM};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(x), gdim, gstr, box, estr,

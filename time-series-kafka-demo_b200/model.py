@@ -247,7 +247,30 @@ class B200MyCNN(nn.Module):
             raise RuntimeError(f"expected input [B, {self.arch.in_channels}, {self.arch.window}], got {tuple(x.shape)}")
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()                      # predictStream.py:155 casts float64 -> float32
-        return x.contiguous()
+        return x if self._row_pitch(x) else x.contiguous()
+
+    def _row_pitch(self, x: torch.Tensor) -> int:
+        """Row pitch (elements) of a CUDA tensor whose rows are padded by its producer -- a [B, C, W] view of a
+        [B, C, Wp] buffer (see :meth:`empty_windows`) -- or 0 when the tensor has to be taken as contiguous."""
+        if x.device.type != "cuda" or x.dim() != 3 or x.stride(2) != 1 or x.is_contiguous():
+            return 0
+        pitch = x.stride(1)
+        unit = 16 // x.element_size()
+        if pitch < x.shape[2] or pitch % unit or (x.shape[0] > 1 and x.stride(0) != x.shape[1] * pitch) \
+                or (x.data_ptr() % 16):
+            return 0
+        return pitch
+
+    def empty_windows(self, B: int, dtype=torch.bfloat16, device=None) -> torch.Tensor:
+        """A ``[B, C, W]`` window batch whose rows start on 16-byte boundaries whatever W is: a view of a
+        ``[B, C, Wp]`` buffer, ``Wp`` = W rounded up to 8 bf16 / 4 fp32 samples.  A producer that fills THIS tensor
+        (instead of a contiguous one) lets the TMA kernels stream windows with W % 8 != 0 (7500, 37500 ...)
+        straight from it -- no re-pitching copy; the pad is never read."""
+        unit = 16 // torch.empty((), dtype=dtype).element_size()
+        W = self.arch.window
+        Wp = (W + unit - 1) // unit * unit
+        dev = device if device is not None else self._device()
+        return torch.empty(B, self.arch.in_channels, Wp, dtype=dtype, device=dev)[:, :, :W]
 
     def _run(self, x: torch.Tensor, age: torch.Tensor, mode: int, sigmoid: bool) -> torch.Tensor:
         lib, h = self._ensure_handle()
@@ -274,7 +297,12 @@ class B200MyCNN(nn.Module):
             age = age.to(dev)
         out = torch.empty(B, dtype=torch.float32, device=dev)
         ws = self._workspace(lib, h, B, mode, dtype, dev)
-        if torch.cuda.current_device() == dev.index:            # the usual case: no device switch needed
+        pitch = 0 if x.is_contiguous() else self._row_pitch(x)
+        if pitch:                                               # rows padded by the producer: no re-pitching copy
+            with torch.cuda.device(dev):
+                rc = lib.b2cnn_forward_pitched(h, x.data_ptr(), dtype, B, pitch, age.data_ptr(), n_age, mode, int(sigmoid),
+                                               out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        elif torch.cuda.current_device() == dev.index:          # the usual case: no device switch needed
             rc = lib.b2cnn_forward(h, x.data_ptr(), dtype, B, age.data_ptr(), n_age, mode, int(sigmoid),
                                    out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
         else:
@@ -321,12 +349,50 @@ class B200MyCNN(nn.Module):
             raise RuntimeError(f"age must be a scalar or have {B} elements")
         return self._run(window_tensor, age, m, return_prob)
 
+    def call_plan(self, window_tensor: torch.Tensor, age: torch.Tensor, mode: str = "independent",
+                  return_prob: bool = False):
+        """A pre-resolved ``predict()`` for a FIXED pair of device tensors -- the streaming scorer's case: every
+        trigger the ring buffer rewrites the same ``[P, 10, 120]`` tensor and the same ages apply (bin/predictStream.py
+        rebuilds and re-validates everything per row).  Shapes, dtypes, pointers, workspace and the output tensor are
+        resolved once; each call of the returned function is ONE ctypes call (one kernel launch for the production
+        shape) on the then-current CUDA stream and returns the same output tensor.  Re-plan after changing weights,
+        options or tensors."""
+        lib, h = self._ensure_handle()
+        dev = self._handle_device
+        x = self._check_x(window_tensor)
+        if x.device != dev or x.data_ptr() != window_tensor.data_ptr():
+            raise RuntimeError("call_plan needs a float32 / bfloat16 tensor already on the model's device (it is captured by address)")
+        age = age.reshape(-1)
+        if age.device != dev or age.dtype != torch.float32 or not age.is_contiguous() or age.numel() not in (1, x.shape[0]):
+            raise RuntimeError("call_plan needs a contiguous float32 age tensor on the model's device with 1 or B elements")
+        if mode not in ("independent", "sequence"):
+            raise ValueError("mode must be 'independent' or 'sequence'")
+        B = x.shape[0]
+        md = capi.MODE_INDEPENDENT if mode == "independent" else capi.MODE_SEQUENCE
+        dtype = capi.DTYPE_BF16 if x.dtype == torch.bfloat16 else capi.DTYPE_F32
+        out = torch.empty(B, dtype=torch.float32, device=dev)
+        ws = torch.empty(max(int(lib.b2cnn_workspace_bytes_for(h, B, md, dtype)), 256), dtype=torch.uint8, device=dev)
+        pitch = 0 if x.is_contiguous() else self._row_pitch(x)
+        pitch = pitch or self.arch.window
+        args = (h, x.data_ptr(), dtype, B, pitch, age.data_ptr(), age.numel(), md, int(return_prob), out.data_ptr(),
+                ws.data_ptr(), ws.numel())
+        fwd, cur, index, keep = lib.b2cnn_forward_pitched, torch.cuda.current_stream, dev.index, (x, age, ws, self)
+
+        def run():
+            rc = fwd(*args, cur(index).cuda_stream)
+            if rc:
+                capi.check(rc, "b2cnn_forward_pitched")
+            return out
+
+        run.keepalive = keep
+        return run
+
     @torch.no_grad()
     def features(self, x: torch.Tensor) -> torch.Tensor:
         """The tensor after ``x.view(-1, MAGICNUM)`` (bin/models.py:29): [B, L_out] fp32."""
         lib, h = self._ensure_handle()
         dev = self._device()
-        x = self._check_x(x).to(dev)
+        x = self._check_x(x).to(dev).contiguous()
         B = x.shape[0]
         dtype = capi.DTYPE_BF16 if x.dtype == torch.bfloat16 else capi.DTYPE_F32
         feats = torch.empty(B, self.arch.l_out, dtype=torch.float32, device=dev)

@@ -254,12 +254,14 @@ def replay_stream(model, records: Sequence[NumericsRecord], subject_ids: Sequenc
     if age_t.numel() not in (1, P):
         raise RuntimeError(f"ages must be a scalar or have {P} elements")
     rows: List[Tuple[int, float, float]] = []
+    # the ring rewrites ONE [P, 10, 120] tensor per trigger: shapes, pointers and the output buffer are resolved once
+    score = model.call_plan(ring.x, age_t.to(dev), return_prob=True) if hasattr(model, "call_plan") else None
     for i0 in range(0, n, per):
         out = ring.push(raw[:, i0:i0 + per])
         if out is None:
             continue
         x, _, t0 = out
-        prob = model.predict(x, age_t, return_prob=True).cpu().numpy()    # one batched call per trigger
+        prob = (score() if score else model.predict(x, age_t, return_prob=True)).cpu().numpy()    # one batched call per trigger
         for p in range(P):
             if not np.isnan(prob[p]):                                     # predictStream.py:171 drops NaN results
                 rows.append((int(subject_ids[p]), t0, float(prob[p])))
