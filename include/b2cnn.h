@@ -178,7 +178,9 @@ int b2cnn_prep_windows(const int16_t *raw, int64_t n_samples, int32_t n_sig, con
  *   emitted      host int: 1 when x_out was written (from the 10th trigger on), 0 while the first window fills
  * One push may carry at most stride_s seconds of samples.  The ring owns its device buffers; b2cnn_ring_push allocates
  * nothing and is asynchronous on `stream`. */
-enum { B2CNN_SAMPLES_ADC16 = 0, B2CNN_SAMPLES_F64 = 1 };
+enum { B2CNN_SAMPLES_ADC16 = 0, B2CNN_SAMPLES_F64 = 1,
+       B2CNN_SAMPLES_GRID = 2 /* fp64 5-second grid points [n_patients][n_new][n_sig] as bin/processStream.py:126-131 publishes
+                                 them on `call-stream` (already smoothed and filled, 12 per trigger): appended as they are */ };
 typedef struct b2cnn_ring b2cnn_ring;
 int b2cnn_ring_create(const b2cnn_prep_config *cfg, int32_t n_patients, int32_t n_sig, double fs, int32_t device,
                       b2cnn_ring **out);
@@ -190,6 +192,40 @@ int b2cnn_ring_set_signals(b2cnn_ring *ring, int32_t patient, const int32_t *sel
                            const double *baselines, void *stream);
 int b2cnn_ring_push(b2cnn_ring *ring, const void *new_samples, int sample_kind, int64_t n_new, void *x_out, int dtype,
                     int32_t *emitted, int64_t *window_index, double *t0_seconds, void *stream);
+
+/* ---- The reference's wire formats, decoded on the device ----
+ * A trigger's Kafka messages as one DEVICE byte buffer + offsets [n_msgs + 1] (message t = bytes[offsets[t] .. offsets[t+1])).
+ * b2cnn_decode_sample_messages: value = json.dumps([i, val]) (bin/sendStream.py:62): idx_out[t] = i, val_out[t] = val
+ *   (either may be NULL); with `frame` [frame_rows][n_sig] fp64 (first filled with NaN = missing) and row_of_msg[t]
+ *   (the frame row = patient * n_new + sample the message belongs to, from its key / arrival order; < 0 = skip) the
+ *   value is scattered to frame[row][i] -- the array b2cnn_ring_push(B2CNN_SAMPLES_F64) takes.
+ * b2cnn_decode_array_messages: value = "[v0,v1,...]" (bin/processStream.py:128, read back at bin/predictStream.py:241):
+ *   vals_out[t][0 .. max_vals) (NaN-padded), counts_out[t] = number of values (-1: malformed).
+ * Numbers are converted with correct rounding (== json.loads / float() / Double.parseDouble) for up to 19 significant
+ * digits and |decimal exponent| <= 27; NaN / Infinity / null are accepted; anything else counts in *n_bad (device int)
+ * and yields NaN.  b2cnn_parse_decimal is the same parser compiled for the host (tests; status 0 ok, 1 malformed,
+ * 2 out of range). */
+int b2cnn_decode_sample_messages(const void *bytes, const int64_t *offsets, int64_t n_msgs, int32_t *idx_out, double *val_out,
+                                 const int64_t *row_of_msg, double *frame, int64_t frame_rows, int32_t n_sig, int32_t *n_bad,
+                                 void *stream);
+int b2cnn_decode_array_messages(const void *bytes, const int64_t *offsets, int64_t n_msgs, int32_t max_vals, double *vals_out,
+                                int32_t *counts_out, int32_t *n_bad, void *stream);
+double b2cnn_parse_decimal(const char *s, int64_t len, int32_t *status);
+
+/* The B200-native alternative to one JSON message per (sample, signal): ONE binary frame per trigger for all patients.
+ *   header (32 bytes, little-endian)  |  int32 subject_id[n_patients]  |  pad to 8 bytes  |  samples[n_patients][n_new][n_sig]
+ * `kind` = B2CNN_SAMPLES_ADC16 (int16), _F64 or _GRID (fp64): the payload is exactly the array b2cnn_ring_push takes, so
+ * "decoding" is one H2D copy.  b2cnn_frame_check validates a HOST buffer and returns the byte offsets of the two arrays. */
+#define B2CNN_FRAME_MAGIC 0x46573242u /* "B2WF" */
+typedef struct b2cnn_frame_header {
+    uint32_t magic;              /* B2CNN_FRAME_MAGIC */
+    uint16_t version;            /* 1 */
+    uint16_t kind;               /* B2CNN_SAMPLES_* */
+    uint32_t n_patients, n_new, n_sig;
+    uint32_t reserved;
+    uint64_t first_index;        /* index of the frame's first sample (grid point) in the stream: gaps are detectable */
+} b2cnn_frame_header;
+int b2cnn_frame_check(const void *frame, int64_t bytes, b2cnn_frame_header *header_out, int64_t *ids_offset, int64_t *samples_offset);
 
 const char *b2cnn_last_error(void);
 const char *b2cnn_version(void);

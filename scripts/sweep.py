@@ -87,6 +87,7 @@ if __name__ == "__main__":
         print(json.dumps({"arch": "mycnn5", "shape": [P, 10, 120], "dtype": "float32", "ms_per_step": ms, "windows_per_s": P / ms * 1e3,
                           "launches": m.gpu_launches, "hbm_frac_step": P * 4804 / (ms * 1e-3) / 1e9 / peak,
                           "parity_max_rel": float(((y[:64].cpu().double() - want).abs() / den).max()), "parity_n": 64,
+                          "logits_head": [float(v) for v in y[:3].cpu()], "oracle_head": [float(v) for v in want[:3]],
                           "note": "short_batch_kernel: one warp per window, one launch per trigger for all patients"}), flush=True)
     # production shape: MyCNN5 [1,10,120] fp32, latency per call (host-side call overhead included)
     arch = tskd_b200.ARCH_PRESETS["mycnn5"]

@@ -223,7 +223,7 @@ def test_f32_falls_back_to_generic_when_rows_are_not_16_byte_multiples():
     ("mycnn3", 3, 7500, 130, torch.bfloat16, "tensorcore"),
     ("mycnn5", 2, 1533, 300, torch.bfloat16, "tensorcore"),     # odd W
     ("mycnn5", 3, 7501, 70, torch.float32, "stream"),           # fp32: W % 4 != 0 is generic when contiguous, streamed when padded
-    ("mycnn5", 3, 7500, 33, torch.float32, "generic"),          # the generic kernels honour the pitch too
+    ("mycnn5", 3, 7501, 33, torch.float32, "generic"),          # the generic kernels honour the pitch too
     ("mycnn3", 3, 1502, 40, torch.bfloat16, "generic"),         # ... and the single-launch small-window kernel
 ])
 def test_row_padded_windows_need_no_staging_copy(kind, C, W, B, dtype, path):

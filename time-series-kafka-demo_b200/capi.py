@@ -18,7 +18,7 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 MODE_INDEPENDENT, MODE_SEQUENCE = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_TENSORCORE = 0, 1, 2
 FLAG_AFFINE = 1
-SAMPLES_ADC16, SAMPLES_F64 = 0, 1
+SAMPLES_ADC16, SAMPLES_F64, SAMPLES_GRID = 0, 1, 2
 
 # every symbol include/b2cnn.h declares (tests/test_host.py::test_library_exports_every_declared_symbol checks the list)
 SYMBOLS = ("b2cnn_l_out", "b2cnn_weight_count", "b2cnn_create", "b2cnn_destroy",
@@ -26,7 +26,8 @@ SYMBOLS = ("b2cnn_l_out", "b2cnn_weight_count", "b2cnn_create", "b2cnn_destroy",
            "b2cnn_features", "b2cnn_set_option", "b2cnn_get_option", "b2cnn_last_launch_count",
            "b2cnn_last_path", "b2cnn_last_stage_ms", "b2cnn_last_error", "b2cnn_version",
            "b2cnn_prep_window_count", "b2cnn_prep_workspace_bytes", "b2cnn_prep_windows",
-           "b2cnn_ring_create", "b2cnn_ring_destroy", "b2cnn_ring_reset", "b2cnn_ring_set_signals", "b2cnn_ring_push")
+           "b2cnn_ring_create", "b2cnn_ring_destroy", "b2cnn_ring_reset", "b2cnn_ring_set_signals", "b2cnn_ring_push",
+           "b2cnn_decode_sample_messages", "b2cnn_decode_array_messages", "b2cnn_parse_decimal", "b2cnn_frame_check")
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -38,6 +39,15 @@ class Config(ctypes.Structure):
                 ("in_channels", "k1", "c_mid", "k2", "pool_k", "pool_s", "hidden", "layers",
                  "window", "lstm_input", "act", "flags")] + \
                [("age_coef", ctypes.c_float), ("device", ctypes.c_int32)]
+
+
+class FrameHeader(ctypes.Structure):
+    """b2cnn_frame_header: one binary frame per trigger for all patients (include/b2cnn.h)."""
+    _fields_ = [("magic", ctypes.c_uint32), ("version", ctypes.c_uint16), ("kind", ctypes.c_uint16), ("n_patients", ctypes.c_uint32),
+                ("n_new", ctypes.c_uint32), ("n_sig", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("first_index", ctypes.c_uint64)]
+
+
+FRAME_MAGIC = 0x46573242
 
 
 class PrepConfig(ctypes.Structure):
@@ -98,6 +108,13 @@ def load_library() -> ctypes.CDLL:
     lib.b2cnn_ring_push.argtypes = [c_vp, c_vp, c_int, c_i64, c_vp, c_int, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64),
                                     ctypes.POINTER(ctypes.c_double), c_vp]
     lib.b2cnn_ring_push.restype = c_int
+    lib.b2cnn_decode_sample_messages.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]
+    lib.b2cnn_decode_sample_messages.restype = c_int
+    lib.b2cnn_decode_array_messages.argtypes = [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]
+    lib.b2cnn_decode_array_messages.restype = c_int
+    lib.b2cnn_parse_decimal.argtypes = [ctypes.c_char_p, c_i64, ctypes.POINTER(c_i32)]; lib.b2cnn_parse_decimal.restype = ctypes.c_double
+    lib.b2cnn_frame_check.argtypes = [c_vp, c_i64, ctypes.POINTER(FrameHeader), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+    lib.b2cnn_frame_check.restype = c_int
     lib.b2cnn_last_error.argtypes = []; lib.b2cnn_last_error.restype = ctypes.c_char_p
     lib.b2cnn_version.argtypes = []; lib.b2cnn_version.restype = ctypes.c_char_p
     _lib = lib

@@ -174,16 +174,60 @@ extern "C" int b2cnn_ring_set_signals(b2cnn_ring *h, int32_t patient, const int3
 extern "C" int b2cnn_ring_push(b2cnn_ring *h, const void *new_samples, int sample_kind, int64_t n_new, void *x_out, int dtype,
                                int32_t *emitted, int64_t *window_index, double *t0_seconds, void *stream) {
     if (!h) return fail(B2CNN_EINVAL, "b2cnn_ring_push: null argument");
-    if (sample_kind != B2CNN_SAMPLES_ADC16 && sample_kind != B2CNN_SAMPLES_F64)
-        return fail(B2CNN_EINVAL, "b2cnn_ring_push: sample_kind must be B2CNN_SAMPLES_ADC16 or B2CNN_SAMPLES_F64");
+    if (sample_kind != B2CNN_SAMPLES_ADC16 && sample_kind != B2CNN_SAMPLES_F64 && sample_kind != B2CNN_SAMPLES_GRID)
+        return fail(B2CNN_EINVAL, "b2cnn_ring_push: sample_kind must be B2CNN_SAMPLES_ADC16, _F64 or _GRID");
     DEVICE_GUARD(h->device);
     const char *err = "";
     int em = 0;
-    const int rc = ring_push(h->r, new_samples, sample_kind == B2CNN_SAMPLES_ADC16, n_new, x_out, dtype, &em, window_index,
+    const int rc = ring_push(h->r, new_samples, sample_kind, n_new, x_out, dtype, &em, window_index,
                              t0_seconds, reinterpret_cast<cudaStream_t>(stream), &err);
     if (rc != B2CNN_OK) return fail(rc, std::string("b2cnn_ring_push: ") + err);
     if (emitted) *emitted = em;
     return B2CNN_OK;
+}
+
+// ---- wire formats (b2cnn_wire.cu) ----
+extern "C" int b2cnn_decode_sample_messages(const void *bytes, const int64_t *offsets, int64_t n_msgs, int32_t *idx_out, double *val_out,
+                                            const int64_t *row_of_msg, double *frame, int64_t frame_rows, int32_t n_sig, int32_t *n_bad,
+                                            void *stream) {
+    const char *err = "";
+    const int rc = wire_decode_pairs(reinterpret_cast<const uint8_t *>(bytes), offsets, n_msgs, idx_out, val_out, row_of_msg, frame,
+                                     frame_rows, n_sig, n_bad, reinterpret_cast<cudaStream_t>(stream), &err);
+    return rc == B2CNN_OK ? rc : fail(rc, std::string("b2cnn_decode_sample_messages: ") + err);
+}
+extern "C" int b2cnn_decode_array_messages(const void *bytes, const int64_t *offsets, int64_t n_msgs, int32_t max_vals, double *vals_out,
+                                           int32_t *counts_out, int32_t *n_bad, void *stream) {
+    const char *err = "";
+    const int rc = wire_decode_arrays(reinterpret_cast<const uint8_t *>(bytes), offsets, n_msgs, max_vals, vals_out, counts_out, n_bad,
+                                      reinterpret_cast<cudaStream_t>(stream), &err);
+    return rc == B2CNN_OK ? rc : fail(rc, std::string("b2cnn_decode_array_messages: ") + err);
+}
+extern "C" int b2cnn_frame_check(const void *frame, int64_t bytes, b2cnn_frame_header *header_out, int64_t *ids_offset,
+                                 int64_t *samples_offset) {
+    if (!frame || bytes < (int64_t)sizeof(b2cnn_frame_header)) return fail(B2CNN_EINVAL, "b2cnn_frame_check: buffer shorter than a header");
+    b2cnn_frame_header hd;
+    memcpy(&hd, frame, sizeof hd);
+    if (hd.magic != B2CNN_FRAME_MAGIC || hd.version != 1) return fail(B2CNN_EINVAL, "b2cnn_frame_check: bad magic / version");
+    if (hd.kind > B2CNN_SAMPLES_GRID || hd.n_patients < 1 || hd.n_new < 1 || hd.n_sig < 1 || hd.n_sig > 64)
+        return fail(B2CNN_EINVAL, "b2cnn_frame_check: bad kind / shape");
+    const int64_t esz = hd.kind == B2CNN_SAMPLES_ADC16 ? 2 : 8;
+    const int64_t ids = sizeof hd, smp = (ids + 4ll * hd.n_patients + 7) / 8 * 8;
+    const int64_t need = smp + esz * hd.n_patients * hd.n_new * hd.n_sig;
+    if (bytes != need) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "b2cnn_frame_check: frame is %lld bytes, its header describes %lld", (long long)bytes, (long long)need);
+        return fail(B2CNN_EINVAL, buf);
+    }
+    if (header_out) *header_out = hd;
+    if (ids_offset) *ids_offset = ids;
+    if (samples_offset) *samples_offset = smp;
+    return B2CNN_OK;
+}
+extern "C" double b2cnn_parse_decimal(const char *s, int64_t len, int32_t *status) {
+    int st = 0;
+    const double v = wire_parse_decimal_host(s, len, &st);
+    if (status) *status = st;
+    return v;
 }
 
 extern "C" const char *b2cnn_version(void) { return "b2cnn 0.3 (sm_100a; tcgen05 fused bf16 path, fp32 streaming path, generic path, device preprocessing + patient ring buffers)"; }

@@ -328,6 +328,7 @@ static int launch_frontend_impl(const Dims &d, const ConvWeights &cw, const void
     int gy = (2 * num_sms + gx - 1) / gx;
     if (gy > B) gy = (int)B;
     if (win_list && gy > 16) gy = 16;          // the exception path: few windows expected
+    if (gate_part && gy > 4) gy = 4;           // ... and its (normally empty) launch sits on the critical path of every forward
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
     dim3 grid(gx, gy);

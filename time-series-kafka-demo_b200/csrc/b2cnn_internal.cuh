@@ -143,8 +143,16 @@ int ring_device(const Ring *r);
 int ring_reset(Ring *r, cudaStream_t st, const char **err);
 int ring_set_signals(Ring *r, int patient, const int *sel, int n_sel, const double *gains, const double *baselines,
                      cudaStream_t st, const char **err);
-int ring_push(Ring *r, const void *new_samples, int in_is_adc, int64_t n_new, void *x_out, int dtype, int *emitted,
+int ring_push(Ring *r, const void *new_samples, int sample_kind, int64_t n_new, void *x_out, int dtype, int *emitted,
               int64_t *window_out, double *t0_out, cudaStream_t st, const char **err);
+
+// b2cnn_wire.cu: the reference's JSON wire formats decoded on the device (row f3)
+int wire_decode_pairs(const uint8_t *bytes, const int64_t *offsets, int64_t n_msgs, int *idx_out, double *val_out,
+                      const int64_t *row_of_msg, double *frame, int64_t frame_rows, int n_sig, int *n_bad, cudaStream_t st,
+                      const char **err);
+int wire_decode_arrays(const uint8_t *bytes, const int64_t *offsets, int64_t n_msgs, int max_vals, double *vals_out, int *counts_out,
+                       int *n_bad, cudaStream_t st, const char **err);
+double wire_parse_decimal_host(const char *s, int64_t len, int *status);
 
 void launch_transpose_wih(const float *wih0, float *wih0T, int L, cudaStream_t st);
 

@@ -228,8 +228,8 @@ constexpr int kRingGrid = 256;          // grid ring capacity (>= window_points 
 struct RingPush {
     double *samples, *grid, *last, *first;      // ring state (see above)
     const int *col; const double *gain, *base; const int *n_sel;   // [P][16] signal selection per patient
-    const void *in;                             // new samples [P][n_new][n_sig]: int16 ADC units or fp64 physical
-    int in_is_adc;
+    const void *in;                             // new samples [P][n_new][n_sig]: int16 ADC units or fp64 physical,
+    int in_is_adc, in_is_grid;                  // or (in_is_grid) fp64 grid points that are already smoothed and filled
     int64_t N0, n_new, R;                       // samples before this push, new samples, sample-ring capacity
     int64_t k0; int n_pts;                      // first new grid index, number of grid points finalised by this push
     int64_t period_ns, grid_ns, smooth_ns;
@@ -245,7 +245,17 @@ ring_push_kernel(RingPush a) {
     double *smp = a.samples + (int64_t)p * a.R * a.n_sig;
     double *grid = a.grid + (int64_t)p * a.n_channels * kRingGrid;
     const int nsel = a.n_sel[p];
+    if (a.in_is_grid) {
+        // bin/processStream.py already did the smoothing and the fills: the points go straight into the grid ring
+        const double *in = reinterpret_cast<const double *>(a.in) + (int64_t)p * a.n_new * a.n_sig;
+        for (int e = tid; e < nsel * a.n_pts; e += blockDim.x) {
+            const int c = e / a.n_pts, q = e - c * a.n_pts;
+            grid[c * kRingGrid + (int)((a.k0 + q) % kRingGrid)] = in[(int64_t)q * a.n_sig + a.col[p * 16 + c]];
+        }
+        __syncthreads();
+    }
     // ---- 1. the new samples -> physical values -> sample ring
+    if (!a.in_is_grid)
     for (int64_t e = tid; e < a.n_new * a.n_sig; e += blockDim.x) {
         const int64_t i = e / a.n_sig; const int sg = (int)(e - i * a.n_sig);
         double v;
@@ -261,6 +271,7 @@ ring_push_kernel(RingPush a) {
     __syncthreads();
     // ---- 2. the grid points this push finalises: direct window sums in time order (as prep_grid_kernel)
     const int64_t N1 = a.N0 + a.n_new;
+    if (!a.in_is_grid)
     for (int e = tid; e < nsel * a.n_pts; e += blockDim.x) {
         const int c = e / a.n_pts, q = e - c * a.n_pts;
         const int64_t tau = (a.k0 + q) * a.grid_ns;
@@ -277,7 +288,7 @@ ring_push_kernel(RingPush a) {
     }
     __syncthreads();
     // ---- 3. forward fill across pushes (one thread per channel, sequential over <= 64 points)
-    if (tid < nsel) {
+    if (!a.in_is_grid && tid < nsel) {
         double last = a.last[p * 16 + tid], first = a.first[p * 16 + tid];
         for (int q = 0; q < a.n_pts; ++q) {
             double v = s_pts[tid][q];
@@ -387,16 +398,20 @@ int ring_set_signals(Ring *r, int patient, const int *sel, int n_sel, const doub
 
 // One trigger.  Returns B2CNN_OK; *emitted = 1 when x_out[n_patients][n_channels][window_points] was written (window index
 // *window_out, start time *t0_out seconds), 0 while the first 600 s are still filling.
-int ring_push(Ring *r, const void *new_samples, int in_is_adc, int64_t n_new, void *x_out, int dtype, int *emitted,
+int ring_push(Ring *r, const void *new_samples, int sample_kind, int64_t n_new, void *x_out, int dtype, int *emitted,
               int64_t *window_out, double *t0_out, cudaStream_t st, const char **err) {
     if (!new_samples || !x_out || !emitted || n_new < 1) { *err = "null pointer / n_new < 1"; return B2CNN_EINVAL; }
     if (dtype != B2CNN_DTYPE_F32 && dtype != B2CNN_DTYPE_BF16) { *err = "dtype must be f32 or bf16"; return B2CNN_EINVAL; }
-    const int64_t N1 = r->n_samples + n_new;
+    const bool is_grid = sample_kind == B2CNN_SAMPLES_GRID;
+    const int in_is_adc = sample_kind == B2CNN_SAMPLES_ADC16;
+    const int64_t N1 = is_grid ? r->n_samples : r->n_samples + n_new;
     const int64_t t_next = N1 * r->period_ns;                        // time of the first sample NOT yet received
-    const int64_t k_end = t_next / r->grid_ns;                       // grid points 0 .. k_end-1 are final
+    const int64_t k_end = is_grid ? r->k_done + n_new : t_next / r->grid_ns;   // grid points 0 .. k_end-1 are final
     const int64_t n_pts = k_end - r->k_done;
-    if (n_pts > kRingMaxNewPts || n_new * r->period_ns > (int64_t)r->cfg.stride_s * 1000000000ll + r->period_ns) {
-        *err = "one push may carry at most stride_s seconds of samples"; return B2CNN_EINVAL;
+    const int step_pts = r->cfg.stride_s / r->cfg.grid_s;
+    if (n_pts > kRingMaxNewPts || (is_grid && n_new > step_pts) ||
+        (!is_grid && n_new * r->period_ns > (int64_t)r->cfg.stride_s * 1000000000ll + r->period_ns)) {
+        *err = "one push may carry at most stride_s seconds of samples / grid points"; return B2CNN_EINVAL;
     }
     const int step = r->cfg.stride_s / r->cfg.grid_s;
     const int64_t w_last_k = r->w_next * step + r->cfg.window_points - 1;
@@ -404,7 +419,7 @@ int ring_push(Ring *r, const void *new_samples, int in_is_adc, int64_t n_new, vo
     RingPush a;
     a.samples = r->d_samples; a.grid = r->d_grid; a.last = r->d_last; a.first = r->d_first;
     a.col = r->d_col; a.gain = r->d_gain; a.base = r->d_base; a.n_sel = r->d_nsel;
-    a.in = new_samples; a.in_is_adc = in_is_adc; a.N0 = r->n_samples; a.n_new = n_new; a.R = r->R;
+    a.in = new_samples; a.in_is_adc = in_is_adc; a.in_is_grid = is_grid ? 1 : 0; a.N0 = r->n_samples; a.n_new = n_new; a.R = r->R;
     a.k0 = r->k_done; a.n_pts = (int)n_pts;
     a.period_ns = r->period_ns; a.grid_ns = r->grid_ns; a.smooth_ns = r->smooth_ns;
     a.n_sig = r->n_sig; a.n_channels = r->cfg.n_channels; a.window_points = r->cfg.window_points;

@@ -204,9 +204,10 @@ class PatientRing:
         from . import capi
         capi.check(self._lib.b2cnn_ring_reset(self._h, None), "b2cnn_ring_reset")
 
-    def push(self, new_samples):
+    def push(self, new_samples, grid_points: bool = False):
         """``new_samples`` [P, n_new, n_sig]: int16 ADC units (WFDB format 16, -32768 = missing) or float64 physical
-        values (NaN = missing), host or device.  Returns ``(x [P,10,120] on the device, window_index, t0_seconds)`` or
+        values (NaN = missing), host or device; with ``grid_points`` the rows are 5-second grid points that
+        bin/processStream.py already smoothed and filled (the ``call-stream`` payload).  Returns ``(x [P,10,120] on the device, window_index, t0_seconds)`` or
         ``None`` while the first window is still filling.  The returned tensor is reused by the next push."""
         import ctypes
 
@@ -216,7 +217,9 @@ class PatientRing:
         t = torch.as_tensor(new_samples)
         if t.dim() == 2:
             t = t.unsqueeze(0)
-        if t.dtype == torch.int16:
+        if grid_points:
+            kind, t = capi.SAMPLES_GRID, t.to(torch.float64)
+        elif t.dtype == torch.int16:
             kind = capi.SAMPLES_ADC16
         else:
             kind, t = capi.SAMPLES_F64, t.to(torch.float64)
@@ -267,3 +270,96 @@ def replay_stream(model, records: Sequence[NumericsRecord], subject_ids: Sequenc
                 rows.append((int(subject_ids[p]), t0, float(prob[p])))
     ring.close()
     return rows
+
+
+# ---------------------------------------------------------------------------------------------- wire formats (row f3)
+def _message_buffer(values, device):
+    """A trigger's message values (a sequence of bytes objects, or one bytes buffer + offsets) as device tensors."""
+    import torch
+    if isinstance(values, tuple):
+        buf, offs = values
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+    else:
+        lens = np.fromiter((len(v) for v in values), dtype=np.int64, count=len(values))
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        buf = b"".join(values)
+    b = torch.frombuffer(bytearray(buf) if len(buf) else bytearray(1), dtype=torch.uint8).to(device)
+    return b, torch.from_numpy(offs).to(device), len(offs) - 1
+
+
+def decode_sample_messages(values, rows, n_rows: int, n_sig: int, device="cuda"):
+    """The ``[i, val]`` messages of bin/sendStream.py:59-64, decoded on the device and scattered into the fp64 frame
+    ``[n_rows, n_sig]`` (NaN = no message / missing) that ``PatientRing.push`` takes.  ``rows[t]`` = frame row of message t
+    (patient * n_new + sample, from the message key and arrival order).  Returns (frame, number of malformed messages)."""
+    import torch
+
+    from . import capi
+    lib = capi.load_library()
+    dev = torch.device(device)
+    b, offs, n = _message_buffer(values, dev)
+    rows_t = torch.as_tensor(np.ascontiguousarray(rows, dtype=np.int64)).to(dev)
+    frame = torch.empty((n_rows, n_sig), dtype=torch.float64, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        capi.check(lib.b2cnn_decode_sample_messages(b.data_ptr(), offs.data_ptr(), n, None, None, rows_t.data_ptr(), frame.data_ptr(),
+                                                    n_rows, n_sig, bad.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "b2cnn_decode_sample_messages")
+        for t in (b, offs, rows_t):
+            t.record_stream(torch.cuda.current_stream())
+    return frame, int(bad.item())
+
+
+def decode_array_messages(values, max_vals: int = 12, device="cuda"):
+    """The ``[v0,v1,...]`` messages of bin/processStream.py:126-131 (12 grid points per patient, channel and trigger),
+    decoded on the device.  Returns (vals [n_msgs, max_vals] fp64 NaN-padded, counts [n_msgs], malformed)."""
+    import torch
+
+    from . import capi
+    lib = capi.load_library()
+    dev = torch.device(device)
+    b, offs, n = _message_buffer(values, dev)
+    vals = torch.empty((n, max_vals), dtype=torch.float64, device=dev)
+    counts = torch.empty((n,), dtype=torch.int32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        capi.check(lib.b2cnn_decode_array_messages(b.data_ptr(), offs.data_ptr(), n, max_vals, vals.data_ptr(), counts.data_ptr(),
+                                                   bad.data_ptr(), torch.cuda.current_stream().cuda_stream), "b2cnn_decode_array_messages")
+        for t in (b, offs):
+            t.record_stream(torch.cuda.current_stream())
+    return vals, counts, int(bad.item())
+
+
+def pack_frame(subject_ids, samples: np.ndarray, first_index: int = 0, grid_points: bool = False) -> bytes:
+    """One binary frame per trigger for all patients (include/b2cnn.h b2cnn_frame_header): ``samples`` [P, n_new, n_sig]
+    int16 ADC units or float64 -- the array ``PatientRing.push`` takes, so decoding is one copy."""
+    import struct
+
+    from . import capi
+    samples = np.ascontiguousarray(samples)
+    if samples.ndim != 3 or samples.dtype not in (np.int16, np.float64):
+        raise ValueError("samples must be [P, n_new, n_sig] int16 or float64")
+    kind = capi.SAMPLES_GRID if grid_points else (capi.SAMPLES_ADC16 if samples.dtype == np.int16 else capi.SAMPLES_F64)
+    P, n_new, n_sig = samples.shape
+    ids = np.ascontiguousarray(subject_ids, dtype="<i4")
+    if ids.shape != (P,):
+        raise ValueError("one subject id per patient")
+    head = struct.pack("<IHHIIIIQ", capi.FRAME_MAGIC, 1, kind, P, n_new, n_sig, 0, int(first_index))
+    pad = b"\0" * ((-(len(head) + ids.nbytes)) % 8)
+    return head + ids.tobytes() + pad + samples.astype(samples.dtype.newbyteorder("<")).tobytes()
+
+
+def unpack_frame(frame: bytes):
+    """Validates a frame with the library (b2cnn_frame_check) and returns (subject_ids, samples, first_index, grid_points)
+    as zero-copy numpy views of the buffer."""
+    import ctypes
+
+    from . import capi
+    lib = capi.load_library()
+    hd, o_ids, o_smp = capi.FrameHeader(), ctypes.c_int64(0), ctypes.c_int64(0)
+    buf = (ctypes.c_char * len(frame)).from_buffer_copy(frame)
+    capi.check(lib.b2cnn_frame_check(ctypes.addressof(buf), len(frame), ctypes.byref(hd), ctypes.byref(o_ids), ctypes.byref(o_smp)),
+               "b2cnn_frame_check")
+    ids = np.frombuffer(frame, dtype="<i4", count=hd.n_patients, offset=o_ids.value)
+    dt = "<i2" if hd.kind == capi.SAMPLES_ADC16 else "<f8"
+    smp = np.frombuffer(frame, dtype=dt, count=hd.n_patients * hd.n_new * hd.n_sig, offset=o_smp.value)
+    return ids, smp.reshape(hd.n_patients, hd.n_new, hd.n_sig), int(hd.first_index), hd.kind == capi.SAMPLES_GRID
