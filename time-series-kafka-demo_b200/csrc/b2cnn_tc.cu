@@ -640,6 +640,15 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     return launches + n;
 }
 
+#ifdef B2CNN_TIMING
+// experiments only: read and clear the fused kernel's wait counters (cycles summed over warps and CTAs)
+extern "C" int b2cnn_debug_timing(unsigned long long *out16) {
+    if (cudaMemcpyFromSymbol(out16, g_fu_timing, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(g_fu_timing, z, sizeof z) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 bool tc_stream_supported(const TcState &s, const Dims &d, int dtype) {
     return s.ready && s.stream_ready && dtype == B2CNN_DTYPE_F32 && (arch_ok(d) || arch1_ok(d)) && d.C <= 3 && (d.XP % 4) == 0;
 }

@@ -41,6 +41,13 @@ namespace b2cnn {
 #ifndef B2CNN_EPI_SPIN
 #define B2CNN_EPI_SPIN 1                          // epilogue: 1 = spin on the accumulator-ring barrier (A/B: parked 0.5423 -> spinning 0.5297 ms/step)
 #endif
+#ifndef B2CNN_SEGMENTS
+#define B2CNN_SEGMENTS 0                          // 1 = a scheduling fence (pmevent) after every segment of the epilogue iteration (A/B: slower)
+#endif
+#ifndef B2CNN_LDTM_SEG
+#define B2CNN_LDTM_SEG -1                         // segment after which the next block's accumulators are requested (-1: top of the iteration)
+#endif
+constexpr int kLdtmSeg = B2CNN_LDTM_SEG;
 #ifndef B2CNN_UNROLL8
 #define B2CNN_UNROLL8 1                           // epilogue main loop unrolled over one 8-step projection chunk (compile-time indices)
 #endif
@@ -71,6 +78,44 @@ struct TcFusedParams {
     float b2s;                 // conv2 bias * 2 log2 e
 };
 
+// B2CNN_TIMING (experiments only, scripts/fused_timing.py): where the warps of the fused kernel wait.  Every waiting site
+// adds the cycles it spent to a global counter (lane 0 of each warp); b2cnn_debug_timing() reads and clears them.
+//   0 epilogue loop total | 1 TFull spin (conv1 accumulators not ready) | 2 smem-stage wait (tap-9 reads) | 3 PEmpty wait
+//   4 MMA loop total | 5 Full wait (TMA data late) | 6 TEmpty wait (ring full: epilogue behind) | 7 projection waits (W chunk + pieces)
+//   8 producer loop total | 9 Empty wait | 10 epilogue gate drain | 11 launches
+#ifdef B2CNN_TIMING
+__device__ unsigned long long g_fu_timing[16];
+#define FU_T0() const long long t0__ = clock64()
+#define FU_TACC(idx, cond) do { fu_tacc[(idx) & 3] += clock64() - t0__; } while (0)      // per-thread sums, flushed once (FU_TFLUSH)
+#define FU_TDECL() long long fu_tacc[4] = {0, 0, 0, 0}
+#define FU_TFLUSH(base, cond) do { if (cond) for (int i__ = 1; i__ < 4; ++i__) atomicAdd(&g_fu_timing[(base) + i__], (unsigned long long)fu_tacc[i__]); } while (0)
+#else
+#define FU_TDECL() do {} while (0)
+#define FU_TFLUSH(base, cond) do {} while (0)
+#define FU_T0() do {} while (0)
+#define FU_TACC(idx, cond) do {} while (0)
+#endif
+
+// compile-time loop: f(integral_constant<int, I>) for I in [0, N)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+// Segment plan of the epilogue step (see the iteration body): which segment runs phase 1 of activation pair p (phases 2
+// and 3 follow one and two segments later), the two conv2 chain steps of each of the first five B segments, and the
+// five pieces of stage B's tail.  MUFU per segment -- plan 0: 2 3 3 3 3 5 5 3 1 0, plan 1: 2 3 3 3 3 3 2 2 3 3 1 0.
+#ifndef B2CNN_SEGPLAN
+#define B2CNN_SEGPLAN 1
+#endif
+struct SegPlan {
+    // MUFU per segment (plan 1): 2 2 4 3 3 3 3 3 3 1 1 0 0
+    static constexpr int kSegs = 13;
+    static constexpr int kDist = 2;                                                  // segments between a MUFU and its consumer's segment
+    __host__ __device__ static constexpr int a1(int p) { return p + 1; }             // phase 1 of activation pair p (phases 2, 3: + kDist, + 2 kDist)
+    __host__ __device__ static constexpr int conv2(int i) { return i; }              // chain step i (q2 = i / 5, tap k = i % 5) of the 10
+    __host__ __device__ static constexpr int tail(int i) { return i < 3 ? 2 * i : i + 2; }   // pool2+exp | rcp | hi piece | mid piece | lo piece: 0 2 4 5 6
+};
+
 // barrier indices (uint64_t slots)
 struct FuBars {
     // per window tile t (stride kPerTile)
@@ -86,6 +131,9 @@ template <int C, int SPLITS, int ARCH>
 __global__ void __launch_bounds__(kFuThreads, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcFusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+#ifdef B2CNN_TIMING
+    const long long t_entry = clock64();
+#endif
     // [2 tiles][2 stages][C][16 KB] | bands | W ring [2][6 KB] | barriers | tmem slot
     uint8_t *sA = smem;
     uint8_t *sBm = sA + 2 * 2 * C * kTcABytes;
@@ -135,17 +183,25 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     if (warp == 0) {
         // ===================== producer =====================
         if (lane == 0) {
+            FU_TDECL();
+#ifdef B2CNN_TIMING
+            const long long tp0 = clock64();
+#endif
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i & 1, ph = (i >> 1) & 1;
                 for (int t = 0; t < 2; ++t) {
                     const int o = t * FuBars::kPerTile;
-                    mbar_wait_parked(BAR(o + FuBars::kEmpty + s), ph ^ 1);
+                    { FU_T0(); mbar_wait_parked(BAR(o + FuBars::kEmpty + s), ph ^ 1); FU_TACC(9, true); }
                     mbar_expect_tx(BAR(o + FuBars::kFull + s), C * kTcABytes);
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         tma_load_3d(smem_u32(sA_of(t, s, c)), &tmap, T0 + kTcAdv * i, c, b_cta + t * kTcM, BAR(o + FuBars::kFull + s));
                 }
             }
+#ifdef B2CNN_TIMING
+            atomicAdd(&g_fu_timing[8], (unsigned long long)(clock64() - tp0));
+#endif
+            FU_TFLUSH(8, true);
         }
     } else if (warp == 1 || warp == 2) {
         // ===================== MMA issuer of window tile t =====================
@@ -153,6 +209,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         // elected lane issues the tcgen05 instructions.  Descriptors are base + small offsets.
         const int t = warp - 1;
         const int o = t * FuBars::kPerTile;
+        FU_TDECL();
         const uint64_t a_base = desc_sw128_kmajor(smem_u32(sA_of(t, 0, 0)));
         const uint64_t b_base = desc_none_kmajor(smem_u32(sBm), 128, 256);
         const uint64_t w_base = desc_none_kmajor(smem_u32(sW), 128, 256);
@@ -162,8 +219,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint32_t tcol = tmem_base + t * 256;
         auto issue_proj = [&](int m) {
             const int u = m & 1, ph = (m >> 1) & 1;
+            { FU_T0();
             mbar_wait_parked(BAR(FuBars::kWFull + u), ph);
             mbar_wait_parked(BAR(o + FuBars::kPFull + u), ph);
+            FU_TACC(7, lane == 0); }
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t d = tcol + 192;
@@ -182,6 +241,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             __syncwarp();
         };
         int m_done = 0, n = 0, i = 0;
+#ifdef B2CNN_TIMING
+        const long long tm0 = clock64();
+#endif
         for (int j = 0; j < J; ++j) {
             const int s = i & 1, slot = j & 3;
             if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done); ++m_done; }
@@ -189,8 +251,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             if (n == 0) mbar_wait(BAR(o + FuBars::kFull + s), (i >> 1) & 1);
             mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
 #else
-            if (n == 0) mbar_wait_parked(BAR(o + FuBars::kFull + s), (i >> 1) & 1);
-            mbar_wait_parked(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
+            { FU_T0(); if (n == 0) mbar_wait_parked(BAR(o + FuBars::kFull + s), (i >> 1) & 1); FU_TACC(5, lane == 0); }
+            { FU_T0(); mbar_wait_parked(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1); FU_TACC(6, lane == 0); }
 #endif
             tc_fence_after();
             if (elect_one()) {
@@ -216,6 +278,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             if (++n == kTcBlocks) { n = 0; ++i; }
         }
         for (; m_done < nchunks; ++m_done) issue_proj(m_done);
+#ifdef B2CNN_TIMING
+        if (lane == 0) atomicAdd(&g_fu_timing[4], (unsigned long long)(clock64() - tm0));
+#endif
+        FU_TFLUSH(4, lane == 0);
         if (elect_one()) umma_commit(BAR(o + FuBars::kGFull));
         __syncwarp();
     } else if (warp == 3) {
@@ -234,10 +300,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
     } else {
         // ===================== epilogue: thread == window =====================
-        // Software-pipelined by one step: iteration jj runs stage A of block jj (TMEM -> pool1 ->
-        // tanh) and stage B of step jj-1 (conv2 -> pool2 -> tanh -> bf16 pieces -> TMEM).  The two
-        // stages touch disjoint registers, so their MUFU / FMA chains interleave in one basic block;
-        // all barrier traffic sits at the top and bottom of the iteration.
+        // Software-pipelined over three steps.  Iteration jj runs
+        //   stage A  of block jj    TMEM -> pool1 -> tanh, kept as r = (1 - tanh)/2           -> a1 registers
+        //   stage Bc of step  jj-1  conv2 over a1(jj-2), a1(jj-1)                             -> 4 conv2 outputs
+        //   stage Bt of step  jj-2  pool2 -> tanh -> three bf16 pieces -> tcgen05.st (A operand of the projection)
+        // The stages touch disjoint registers; every dependent chain of one stage (MUFU -> FADD2 -> FMUL -> MUFU ...,
+        // the 10-deep conv2 FMA chains, the piece splitting) has the other two stages' work to hide behind.  All barrier
+        // traffic sits at the top and bottom of the iteration.
         const int t = (warp - 4) >> 2;
         const int o_bar = t * FuBars::kPerTile;
         const int q = warp & 3;
@@ -246,9 +315,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
         const uint32_t swz = (uint32_t)(row & 7);
         const bool row_ok = b < p.B;
+        FU_TDECL();
         // a1 history: abuf[jj & 1] holds the 4 activations x 4 channels produced by stage A of block jj
         // all per-channel state is held as float2 over channel pairs (0,1) and (2,3)
         float2 pm6[2], pm7[2], abuf[2][4][2];
+        float c2s[2][4];                                    // conv2 outputs: Bc of iteration jj writes c2s[jj & 1], Bt of jj + 1 reads them
         float c2c = 0.f;
 #pragma unroll
         for (int q2 = 0; q2 < 2; ++q2) {
@@ -256,6 +327,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 4; ++i) { abuf[0][i][q2] = make_float2(0.f, 0.f); abuf[1][i][q2] = make_float2(0.f, 0.f); }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { c2s[0][i] = 0.f; c2s[1][i] = 0.f; }
         // accumulator registers are double-buffered by step parity (block jj lives in Dbuf[jj & 1]; the
         // next block's tcgen05.ld is issued into the other half) -- no register-to-register copies
         uint32_t Dbuf[2][32];
@@ -269,45 +342,57 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 5; ++k) w2r[q2][k] = p.w2p[q2][k];
 
-        // KK >= 0: the step's index inside its 8-step projection chunk is a compile-time constant (the main loop is
-        // unrolled over one chunk): accumulator-ring slots, barrier addresses and parities, the A-operand column and
-        // the chunk-boundary branches all fold, which removes about a third of the loop's instructions (they were
-        // uniform-datapath address / parity arithmetic and branches, not math).  KK == -1: the same step with
+        // KK >= 0: (jj - 1) & 7 is a compile-time constant (the main loop is unrolled over the eight steps whose features
+        // fill one 16-position projection chunk): accumulator-ring slots, barrier addresses and parities, the A-operand
+        // column and the chunk-boundary branches all fold, which removes about a third of the loop's instructions (they
+        // were uniform-datapath address / parity arithmetic and branches, not math).  KK == -1: the same iteration with
         // everything computed at run time (prologue, the tail after the last whole chunk).
-        auto iteration = [&](int jj, int m, auto doA_, auto doB_, auto par_, auto kk_) {
-            constexpr bool doA = decltype(doA_)::value, doB = decltype(doB_)::value;
+        // m = chunk of step jj - 2 (the one whose features this iteration stores).
+        auto iteration = [&](int jj, int m, auto doA_, auto doBc_, auto doBt_, auto par_, auto kk_) {
+            constexpr bool doA = decltype(doA_)::value, doBc = decltype(doBc_)::value, doBt = decltype(doBt_)::value;
             constexpr int PAR = decltype(par_)::value;      // == jj & 1 (compile-time register naming)
             constexpr int KK = decltype(kk_)::value;        // == (jj - 1) & 7, or -1
             const int s = ti & 1;
-            const int jb = jj - 1, kk = KK >= 0 ? KK : (jb & 7), u = m & 1;
+            const int jt = jj - 2, kk = KK >= 0 ? ((KK + 7) & 7) : (jt & 7), u = m & 1;   // stored step, its column, its A buffer
             const int slot0 = KK >= 0 ? ((KK + 1) & 3) : (jj & 3);                    // ring slot of block jj
             const int slot1 = KK >= 0 ? ((KK + 2) & 3) : ((jj + 1) & 3);              // ... and of block jj + 1
             const int par1 = KK >= 0 ? (((KK + 2) & 7) >> 2) : (((jj + 1) >> 2) & 1);
+            // the next block's accumulators -> the other half of Dbuf (dead since the previous iteration copied its carries out).
+            // kLdtmSeg < 0: at the top of the iteration; else after that segment of the math: the later it is asked for,
+            // the more slack the MMA warp has to refill the ring, as long as the load still lands before the next iteration
+            auto prefetch_next = [&]() {
+                if (KK >= 0 || jj + 1 < J) {
+                    FU_T0();
+#if B2CNN_EPI_SPIN
+                    mbar_wait(BAR(o_bar + FuBars::kTFull + slot1), par1);
+#else
+                    mbar_wait_parked(BAR(o_bar + FuBars::kTFull + slot1), par1);
+#endif
+                    FU_TACC(1, lane == 0);
+                    tc_fence_after();
+                    tmem_ld32_issue(tlane + slot1 * 32, Dbuf[PAR ^ 1]);
+                }
+            };
             // ---------------- top: barriers ----------------
             if constexpr (doA) {
                 tmem_ld32_wait(Dbuf[PAR]);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kTEmpty + slot0));
-                if (KK >= 0 || jj + 1 < J) {                // prefetch the next block's accumulators
-#if B2CNN_EPI_SPIN
-                    mbar_wait(BAR(o_bar + FuBars::kTFull + slot1), par1);
-#else
-                    mbar_wait_parked(BAR(o_bar + FuBars::kTFull + slot1), par1);
-#endif
-                    tc_fence_after();
-                    tmem_ld32_issue(tlane + slot1 * 32, Dbuf[PAR ^ 1]);
-                }
-                if (n == 0) mbar_wait_parked(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1);   // TMA bytes visible for the tap-9 reads
+                if constexpr (kLdtmSeg < 0) prefetch_next();
+                { FU_T0(); if (n == 0) mbar_wait_parked(BAR(o_bar + FuBars::kFull + s), (ti >> 1) & 1); FU_TACC(2, lane == 0); }   // TMA bytes visible for the tap-9 reads
             }
-            if constexpr (doB) {
+            if constexpr (doBt) {
                 if (kk == 0) {                              // first store of chunk m into A buffer u
+                    FU_T0();
                     mbar_wait_parked(BAR(o_bar + FuBars::kPEmpty + u), ((m >> 1) & 1) ^ 1);
+                    FU_TACC(3, lane == 0);
                     tc_fence_after();
                 }
             }
             // ---------------- middle: straight-line math ----------------
             float2 an[4][2];
+            const uint32_t acol = tlane + 128 + u * 24 + kk;
 #if B2CNN_ABLATE == 1
             if constexpr (doA) {
 #pragma unroll
@@ -316,87 +401,137 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     an[r][1] = make_float2(__uint_as_float(Dbuf[PAR][4 + r] ^ Dbuf[PAR][12 + r] ^ Dbuf[PAR][20 + r] ^ Dbuf[PAR][28 + r]), 0.f);
                 }
             }
-            if constexpr (doB) {
+            if constexpr (doBt) {
                 const uint32_t h = __float_as_uint(abuf[PAR][0][0].x) ^ __float_as_uint(abuf[PAR ^ 1][1][1].x);
-                const uint32_t acol = tlane + 128 + u * 24 + kk;
                 tmem_st1(acol, h & 0x3f803f80u);
                 tmem_st1(acol + 8, 0u);
                 tmem_st1(acol + 16, 0u);
             }
 #else
-            if constexpr (doA) {
+            {
+                // The iteration's arithmetic in SegPlan::kSegs segments with a scheduling fence between them.  Left to
+                // itself ptxas sorts the basic block by critical path: the 40 conv2 FFMA2 first, the 28 MUFU (whose results
+                // nothing in the block consumes) in one cluster at the end -- two in-order warps per scheduler then queue
+                // on the 8-cycle MUFU pipe in the same phase while the FMA pipe idles (ncu source view: 40 % of the loop's
+                // samples on that cluster).  Within a segment the MUFUs still sink to the end and their consumers rise to
+                // the top of whatever segment holds them, so consumers sit TWO segments after their producers: one whole
+                // segment of other work covers the MUFU latency.
                 auto Dv = [&](int idx) -> float { return __uint_as_float(Dbuf[PAR][idx]); };
-                if constexpr (ARCH == 0) {
-                    const uint8_t *tile = sA_of(t, s, 0) + row * 128;
+                float2 ex[8], dd[8], acc[4], te = make_float2(0.f, 0.f), tf = make_float2(0.f, 0.f), tr1 = make_float2(0.f, 0.f);
+                float rp[8], trx = 0.f, try_ = 0.f;
+                uint32_t xraw[C];
+                auto segment = [&](auto s_) {
+                    constexpr int S = decltype(s_)::value;
+                    if constexpr (doA) {
+                        if constexpr (ARCH == 0) {
+                            // tap 9 of the previous block's position 7 (it did not fit that block's 16-sample slice)
+                            if constexpr (S == 0) {
+                                const uint8_t *tile = sA_of(t, s, 0) + row * 128;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const uint16_t raw = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
-                        const float xv = __uint_as_float((uint32_t)raw << 16);
+                                for (int c = 0; c < C; ++c)
+                                    xraw[c] = *reinterpret_cast<const uint16_t *>(tile + c * kTcABytes + ((uint32_t)((n + 1) ^ swz) << 4));
+                            }
+                            if constexpr (S == 2) {
 #pragma unroll
-                        for (int q2 = 0; q2 < 2; ++q2) pm7[q2] = fma2(p.w9p[c][q2], make_float2(xv, xv), pm7[q2]);
+                                for (int c = 0; c < C; ++c) {
+                                    const float xv = __uint_as_float(xraw[c] << 16);
+#pragma unroll
+                                    for (int q2 = 0; q2 < 2; ++q2) pm7[q2] = fma2(p.w9p[c][q2], make_float2(xv, xv), pm7[q2]);
+                                }
+                            }
+                        }
+                        static_for<0, 8>([&](auto p_) {
+                            // pair P: pooled position r, out-channels 2*q2, 2*q2+1 (MyCNN5: position 0 needs the carried
+                            // pre-activations pm6 / pm7 and the tap-9 patch, so it goes last)
+                            constexpr int P = decltype(p_)::value;
+                            constexpr int r = ARCH == 0 ? (((P >> 1) + 1) & 3) : (P >> 1), q2 = P & 1, o0 = 2 * q2, o1 = 2 * q2 + 1;
+                            if constexpr (SegPlan::a1(P) == S) {
+                                float2 m2;
+                                if constexpr (ARCH == 0) {
+                                    if constexpr (r == 0) {
+                                        m2 = make_float2(max3_nan(pm6[q2].x, pm7[q2].x, Dv(o0)), max3_nan(pm6[q2].y, pm7[q2].y, Dv(o1)));
+                                    } else {
+                                        constexpr int c0 = 2 * r - 2;
+                                        m2 = make_float2(max3_nan(Dv(c0 * 4 + o0), Dv((c0 + 1) * 4 + o0), Dv((c0 + 2) * 4 + o0)),
+                                                         max3_nan(Dv(c0 * 4 + o1), Dv((c0 + 1) * 4 + o1), Dv((c0 + 2) * 4 + o1)));
+                                    }
+                                } else {
+                                    // pool(2,2): pooled position 4j+i = max(pre[8j+2i], pre[8j+2i+1])
+                                    m2 = make_float2(max_nan(Dv((2 * r) * 4 + o0), Dv((2 * r + 1) * 4 + o0)),
+                                                     max_nan(Dv((2 * r) * 4 + o1), Dv((2 * r + 1) * 4 + o1)));
+                                }
+                                ex[P] = sig_ph1(m2, p.b1sp[q2]);
+                            }
+                            if constexpr (SegPlan::a1(P) + SegPlan::kDist == S) sig_ph2(ex[P], dd[P], rp[P]);
+                            if constexpr (SegPlan::a1(P) + 2 * SegPlan::kDist == S) an[r][q2] = sig_ph3(dd[P], rp[P]);
+                        });
+                        if constexpr (ARCH == 0 && S == SegPlan::a1(7) + 1) {      // after the last reader of pm6 / pm7
+#pragma unroll
+                            for (int q2 = 0; q2 < 2; ++q2) {
+                                pm6[q2] = make_float2(Dv(6 * 4 + 2 * q2), Dv(6 * 4 + 2 * q2 + 1));
+                                pm7[q2] = make_float2(Dv(7 * 4 + 2 * q2), Dv(7 * 4 + 2 * q2 + 1));
+                            }
+                        }
                     }
+                    if constexpr (doBc) {
+                        // conv2 on r = (1 - tanh)/2 (weights pre-multiplied by -2, bias absorbs sum(w)): 40 FFMA2, one
+                        // accumulator per output position over both channel pairs (c2 = acc.x + acc.y)
+                        static_for<0, 10>([&](auto i_) {
+                            constexpr int I = decltype(i_)::value, q2 = I / 5, k = I % 5;
+                            if constexpr (SegPlan::conv2(I) == S) {
+                                // a1(step jj-2) = abuf[PAR], a1(step jj-1) = abuf[PAR ^ 1]
+                                const float2 A8[8] = {abuf[PAR][0][q2], abuf[PAR][1][q2], abuf[PAR][2][q2], abuf[PAR][3][q2],
+                                                      abuf[PAR ^ 1][0][q2], abuf[PAR ^ 1][1][q2], abuf[PAR ^ 1][2][q2], abuf[PAR ^ 1][3][q2]};
 #pragma unroll
-                    for (int q2 = 0; q2 < 2; ++q2) {
-                        const int o0 = 2 * q2, o1 = 2 * q2 + 1;
-                        an[0][q2] = sig_fold2(make_float2(max3_nan(pm6[q2].x, pm7[q2].x, Dv(0 * 4 + o0)),
-                                                           max3_nan(pm6[q2].y, pm7[q2].y, Dv(0 * 4 + o1))), p.b1sp[q2]);
-                        an[1][q2] = sig_fold2(make_float2(max3_nan(Dv(0 * 4 + o0), Dv(1 * 4 + o0), Dv(2 * 4 + o0)),
-                                                           max3_nan(Dv(0 * 4 + o1), Dv(1 * 4 + o1), Dv(2 * 4 + o1))), p.b1sp[q2]);
-                        an[2][q2] = sig_fold2(make_float2(max3_nan(Dv(2 * 4 + o0), Dv(3 * 4 + o0), Dv(4 * 4 + o0)),
-                                                           max3_nan(Dv(2 * 4 + o1), Dv(3 * 4 + o1), Dv(4 * 4 + o1))), p.b1sp[q2]);
-                        an[3][q2] = sig_fold2(make_float2(max3_nan(Dv(4 * 4 + o0), Dv(5 * 4 + o0), Dv(6 * 4 + o0)),
-                                                           max3_nan(Dv(4 * 4 + o1), Dv(5 * 4 + o1), Dv(6 * 4 + o1))), p.b1sp[q2]);
-                        pm6[q2] = make_float2(Dv(6 * 4 + o0), Dv(6 * 4 + o1));
-                        pm7[q2] = make_float2(Dv(7 * 4 + o0), Dv(7 * 4 + o1));
+                                for (int r = 0; r < 4; ++r) acc[r] = I == 0 ? mul2(w2r[0][0], A8[r]) : fma2(w2r[q2][k], A8[r + k], acc[r]);
+                            }
+                        });
+                        if constexpr (S == SegPlan::conv2(9) + 1) {
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) c2s[PAR][r] = acc[r].x + acc[r].y;
+                        }
                     }
-                } else {
-                    // pool(2,2): pooled position 4j+i = max(pre[8j+2i], pre[8j+2i+1])
-#pragma unroll
-                    for (int q2 = 0; q2 < 2; ++q2) {
-                        const int o0 = 2 * q2, o1 = 2 * q2 + 1;
-#pragma unroll
-                        for (int i2 = 0; i2 < 4; ++i2)
-                            an[i2][q2] = sig_fold2(make_float2(max_nan(Dv((2 * i2) * 4 + o0), Dv((2 * i2 + 1) * 4 + o0)),
-                                                                max_nan(Dv((2 * i2) * 4 + o1), Dv((2 * i2 + 1) * 4 + o1))), p.b1sp[q2]);
+                    if constexpr (doBt) {
+                        const float *c2 = c2s[PAR ^ 1];
+                        if constexpr (S == SegPlan::tail(0)) {      // pool2 + the exponent of tanh
+                            float2 m2;
+                            if constexpr (ARCH == 0) {
+                                m2 = make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3]));
+                                c2c = c2[3];
+                            } else {
+                                m2 = make_float2(max_nan(c2[0], c2[1]), max_nan(c2[2], c2[3]));
+                            }
+                            const float2 a = fma2(m2, make_float2(k2Log2e, k2Log2e), make_float2(p.b2s, p.b2s));
+                            B2CNN_EX2(te.x, a.x);
+                            B2CNN_EX2(te.y, a.y);
+                        }
+                        if constexpr (S == SegPlan::tail(1)) {
+                            const float2 d = add2(te, make_float2(1.0f, 1.0f));
+                            B2CNN_RCP(trx, d.x);
+                            B2CNN_RCP(try_, d.y);
+                        }
+                        // three bf16 pieces of (f0, f1) = features 2*jt-FOFF, 2*jt-FOFF+1 -> column kk of this lane's row of the A operand
+                        if constexpr (S == SegPlan::tail(2)) {
+                            tf = fma2(make_float2(trx, try_), make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
+                            const uint32_t h = pack_bf16x2(tf.x, tf.y);
+                            tr1 = sub2(tf, make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u)));
+                            tmem_st1(acol, h);
+                        }
+                        if constexpr (S == SegPlan::tail(3)) {
+                            const uint32_t md = pack_bf16x2(tr1.x, tr1.y);
+                            tf = sub2(tr1, make_float2(__uint_as_float(md << 16), __uint_as_float(md & 0xffff0000u)));
+                            tmem_st1(acol + 8, md);
+                        }
+                        if constexpr (S == SegPlan::tail(4)) tmem_st1(acol + 16, pack_bf16x2(tf.x, tf.y));
                     }
-                }
-            }
-            if constexpr (doB) {
-                // conv2 on r = (1 - tanh)/2 (weights pre-multiplied by -2, bias absorbs sum(w)): 40 FFMA2
-                // one accumulator per output position over both channel pairs: c2 = acc.x + acc.y (no pair-sum step)
-                float2 acc[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int q2 = 0; q2 < 2; ++q2) {
-                    // a1(step jb-1) = abuf[PAR], a1(step jb) = abuf[PAR ^ 1]
-                    const float2 A8[8] = {abuf[PAR][0][q2], abuf[PAR][1][q2], abuf[PAR][2][q2], abuf[PAR][3][q2],
-                                          abuf[PAR ^ 1][0][q2], abuf[PAR ^ 1][1][q2], abuf[PAR ^ 1][2][q2], abuf[PAR ^ 1][3][q2]};
-#pragma unroll
-                    for (int k = 0; k < 5; ++k)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) acc[r] = fma2(w2r[q2][k], A8[r + k], acc[r]);
-                }
-                float c2[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) c2[r] = acc[r].x + acc[r].y;
-                float2 f;                                                    // features 2*jb-FOFF, 2*jb-FOFF+1
-                if constexpr (ARCH == 0) {
-                    f = tanh_fold2(make_float2(max3_nan(c2c, c2[0], c2[1]), max3_nan(c2[1], c2[2], c2[3])), make_float2(p.b2s, p.b2s));
-                    c2c = c2[3];
-                } else {
-                    f = tanh_fold2(make_float2(max_nan(c2[0], c2[1]), max_nan(c2[2], c2[3])), make_float2(p.b2s, p.b2s));
-                }
-                // three bf16 pieces of (f0, f1) -> column kk of this lane's row of the A operand
-                const uint32_t h = pack_bf16x2(f.x, f.y);
-                const float2 r1 = sub2(f, make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u)));
-                const uint32_t md = pack_bf16x2(r1.x, r1.y);
-                const float2 r2 = sub2(r1, make_float2(__uint_as_float(md << 16), __uint_as_float(md & 0xffff0000u)));
-                const uint32_t lo = pack_bf16x2(r2.x, r2.y);
-                const uint32_t acol = tlane + 128 + u * 24 + kk;
-                tmem_st1(acol, h);
-                tmem_st1(acol + 8, md);
-                tmem_st1(acol + 16, lo);
+                };
+                static_for<0, SegPlan::kSegs>([&](auto s_) {
+                    segment(s_);
+                    if constexpr (doA && decltype(s_)::value == kLdtmSeg) prefetch_next();
+#if B2CNN_SEGMENTS
+                    if constexpr (decltype(s_)::value + 1 < SegPlan::kSegs) sched_fence();
+#endif
+                });
             }
 #endif
             if constexpr (doA) {                            // a1(block jj) replaces a1(block jj-2)
@@ -415,8 +550,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                     ++n;
                 }
             }
-            if constexpr (doB) {
-                if (kk == 7 || (KK < 0 && jb == J - 1)) {
+            if constexpr (doBt) {
+                if (kk == 7 || (KK < 0 && jt == J - 1)) {
                     const uint32_t abase = tlane + 128 + u * 24;
                     if (KK < 0)
                         for (int z = kk + 1; z < 8; ++z) { tmem_st1(abase + z, 0u); tmem_st1(abase + z + 8, 0u); tmem_st1(abase + z + 16, 0u); }
@@ -432,31 +567,49 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         using P0 = std::integral_constant<int, 0>;
         using P1 = std::integral_constant<int, 1>;
         using KR = std::integral_constant<int, -1>;
-        iteration(0, 0, T_{}, F_{}, P0{}, KR{});
-        int jj = 1;
+#ifdef B2CNN_TIMING
+        const long long te0 = clock64();
+        if (lane == 0) atomicAdd(&g_fu_timing[12], (unsigned long long)(te0 - t_entry));
+#endif
+        iteration(0, 0, T_{}, F_{}, F_{}, P0{}, KR{});
+        iteration(1, 0, T_{}, T_{}, F_{}, P1{}, KR{});     // J is a multiple of kTcBlocks = 7: blocks 0 and 1 always exist
+        int jj = 2;
 #if B2CNN_UNROLL8
-        // whole chunks whose every step has a successor block (jj + 1 < J): steps 8c .. 8c+7 with compile-time indices
-        const int nfull = J >= 2 ? (J - 2) >> 3 : 0;
+        // whole chunks whose every iteration has a successor block (jj + 1 < J): iterations 8c+2 .. 8c+9 store the features
+        // of steps 8c .. 8c+7 = chunk c, with compile-time indices
+        const int nfull = J >= 11 ? (J - 3) >> 3 : 0;
 #pragma unroll 1
         for (int c = 0; c < nfull; ++c, jj += 8) {
-            iteration(jj + 0, c, T_{}, T_{}, P1{}, std::integral_constant<int, 0>{});
-            iteration(jj + 1, c, T_{}, T_{}, P0{}, std::integral_constant<int, 1>{});
-            iteration(jj + 2, c, T_{}, T_{}, P1{}, std::integral_constant<int, 2>{});
-            iteration(jj + 3, c, T_{}, T_{}, P0{}, std::integral_constant<int, 3>{});
-            iteration(jj + 4, c, T_{}, T_{}, P1{}, std::integral_constant<int, 4>{});
-            iteration(jj + 5, c, T_{}, T_{}, P0{}, std::integral_constant<int, 5>{});
-            iteration(jj + 6, c, T_{}, T_{}, P1{}, std::integral_constant<int, 6>{});
-            iteration(jj + 7, c, T_{}, T_{}, P0{}, std::integral_constant<int, 7>{});
+            iteration(jj + 0, c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 1>{});
+            iteration(jj + 1, c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 2>{});
+            iteration(jj + 2, c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 3>{});
+            iteration(jj + 3, c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 4>{});
+            iteration(jj + 4, c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 5>{});
+            iteration(jj + 5, c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 6>{});
+            iteration(jj + 6, c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 7>{});
+            iteration(jj + 7, c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 0>{});
         }
 #endif
 #pragma unroll 1
-        for (; jj + 1 < J; jj += 2) {                       // two steps per trip: register names alternate
-            iteration(jj, (jj - 1) >> 3, T_{}, T_{}, P1{}, KR{});
-            iteration(jj + 1, jj >> 3, T_{}, T_{}, P0{}, KR{});
+        for (; jj + 1 < J; jj += 2) {                       // two iterations per trip: register names alternate (jj is even here)
+            iteration(jj, (jj - 2) >> 3, T_{}, T_{}, T_{}, P0{}, KR{});
+            iteration(jj + 1, (jj - 1) >> 3, T_{}, T_{}, T_{}, P1{}, KR{});
         }
-        if (jj < J) { iteration(jj, (jj - 1) >> 3, T_{}, T_{}, P1{}, KR{}); ++jj; }
-        if (J & 1) iteration(J, (J - 1) >> 3, F_{}, T_{}, P1{}, KR{}); else iteration(J, (J - 1) >> 3, F_{}, T_{}, P0{}, KR{});
+        if (jj < J) { iteration(jj, (jj - 2) >> 3, T_{}, T_{}, T_{}, P0{}, KR{}); ++jj; }
+        // jj == J: drain the pipeline (conv2 of step J-1, features of steps J-2 and J-1)
+        if (J & 1) {
+            iteration(J, (J - 2) >> 3, F_{}, T_{}, T_{}, P1{}, KR{});
+            iteration(J + 1, (J - 1) >> 3, F_{}, F_{}, T_{}, P0{}, KR{});
+        } else {
+            iteration(J, (J - 2) >> 3, F_{}, T_{}, T_{}, P0{}, KR{});
+            iteration(J + 1, (J - 1) >> 3, F_{}, F_{}, T_{}, P1{}, KR{});
+        }
 
+#ifdef B2CNN_TIMING
+        if (lane == 0) atomicAdd(&g_fu_timing[0], (unsigned long long)(clock64() - te0));
+        const long long tg0 = clock64();
+#endif
+        FU_TFLUSH(0, lane == 0);
         // ---- gate pre-activations of this CTA's position range -> partial[range][window][64]
         mbar_wait_parked(BAR(o_bar + FuBars::kGFull), 0);
         tc_fence_after();
@@ -479,6 +632,11 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
         // up to n_ranges CTAs may flag the same window: the first one appends it to the list of the exact re-computation
         if (row_ok && bad && atomicExch(&p.nanflag[b], 1) == 0) p.list[atomicAdd(p.count, 1)] = b;
+#ifdef B2CNN_TIMING
+        if (lane == 0) atomicAdd(&g_fu_timing[10], (unsigned long long)(clock64() - tg0));
+        if (threadIdx.x == 128 && blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&g_fu_timing[11], 1ull);
+        if (lane == 0) atomicAdd(&g_fu_timing[13], (unsigned long long)(clock64() - t_entry));
+#endif
     }
 
     tc_fence_before();

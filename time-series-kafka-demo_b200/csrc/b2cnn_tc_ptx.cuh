@@ -284,6 +284,32 @@ __device__ __forceinline__ float2 sig_fold2(float2 m, float2 bias_scaled) {
     return make_float2(r0, r1);
 #endif
 }
+// The same activation in three phases, for the segmented epilogue (b2cnn_tc_fused.cuh): a segment issues phase 1 of one
+// pair, phase 2 of the pair before and phase 3 of the pair before that, so every MUFU result has a whole segment of
+// other work between its issue and its first use.
+//   phase 1: e = 2^(clamp(2 log2e (m + bias)))          FFMA2, 2 FMNMX, 2 MUFU.EX2
+//   phase 2: d = e + 1, rp = 1 / (d.x * d.y)            FADD2, FMUL, MUFU.RCP
+//   phase 3: r = rp * (d.y, d.x)                        FMUL2
+__device__ __forceinline__ float2 sig_ph1(float2 m, float2 bias_scaled) {
+    float2 a = fma2(m, make_float2(k2Log2e, k2Log2e), bias_scaled);
+    float e0, e1;
+#if !defined(B2CNN_EXP_NOCLAMP)
+    a.x = min_nan(a.x, 120.0f);
+    a.y = min_nan(a.y, 120.0f);
+#endif
+    B2CNN_EX2(e0, a.x);
+    B2CNN_EX2(e1, a.y);
+    return make_float2(e0, e1);
+}
+__device__ __forceinline__ void sig_ph2(float2 e, float2 &d, float &rp) {
+    d = add2(e, make_float2(1.0f, 1.0f));
+    B2CNN_RCP(rp, d.x * d.y);
+}
+__device__ __forceinline__ float2 sig_ph3(float2 d, float rp) { return mul2(make_float2(rp, rp), make_float2(d.y, d.x)); }
+// scheduling fence: ptxas does not move instructions across a pmevent (SASS PMTRIG, one issue slot, no branch), which
+// is what keeps the segments of the epilogue in source order (b2cnn_tc_fused.cuh)
+__device__ __forceinline__ void sched_fence() { asm volatile("pmevent 1;" ::: "memory"); }
+
 constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
