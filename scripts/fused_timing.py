@@ -35,6 +35,8 @@ print(f"mma:      Full(TMA) {v[5] / mm:.3f}  TEmpty {v[6] / mm:.3f}  proj {v[7] 
 print(f"producer: Empty {v[9] / pr:.3f}")
 nw = max(v[11], 1) * 8 * int(os.environ.get("CTAS", 592))
 print(f"per epilogue warp, cycles: entry->loop {v[12] / nw:.0f}  loop {v[0] / nw:.0f}  gate drain {v[10] / nw:.0f}  lifetime {v[13] / nw:.0f}")
+if v[14]:
+    print(f"CTA 0: {v[14] / max(v[11], 1) / 1e3:.1f} us per launch, SM clock while it ran: {v[15] / v[14] * 1e3:.0f} MHz")
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record()
 for _ in range(N):

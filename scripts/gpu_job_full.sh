@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/g_build.log 2>&1
-timeout -k 10 900 python -m pytest tests -m gpu -q > gpurun_out/g_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/g_pytest.log
+timeout -k 10 900 python -m pytest tests -m gpu -q --timeout 180 > gpurun_out/g_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/g_pytest.log
 tail -6 gpurun_out/g_pytest.log
 timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/g_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/g_smoke.log
 cat gpurun_out/g_smoke.log
@@ -18,8 +18,8 @@ cut -c1-200 gpurun_out/g_bench_b32768.json
 timeout -k 10 900 python scripts/sweep.py > gpurun_out/g_sweep.jsonl 2> gpurun_out/g_sweep.err; echo "sweep rc=$?"; cat gpurun_out/g_sweep.jsonl | cut -c1-330; tail -3 gpurun_out/g_sweep.err
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/g_launches.csv \
     python bench.py --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/g_ncu_launch.log 2>&1
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:tc_fused -s 2 -c 1 -o gpurun_out/g_fused \
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:tc_fused -s 2 -c 1 -f -o gpurun_out/g_fused \
     python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline > gpurun_out/g_ncu_full.log 2>&1
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:stream_f32 -s 2 -c 1 -o gpurun_out/g_stream \
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:stream_f32 -s 2 -c 1 -f -o gpurun_out/g_stream \
     python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu-baseline --dtype f32 > gpurun_out/g_ncu_full_f32.log 2>&1
 ls gpurun_out | grep "^g_"

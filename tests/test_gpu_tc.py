@@ -164,6 +164,26 @@ def test_tc_fused_prefix_and_permutation_consistency():
     assert torch.equal(m.predict(x[perm], ages[perm]), y[perm])
 
 
+@pytest.mark.parametrize("kind,C,W,B", [("mycnn5", 3, 7504, 2100), ("mycnn2", 2, 4000, 4100), ("mycnn5", 3, 1528, 9000)])
+def test_tc_fused_persistent_grid_many_items_per_cta(kind, C, W, B):
+    """More (window-tile pair, position range) items than SMs: every persistent CTA walks several items with different
+    ranges (a shorter last range included), carrying its barrier phases across them.  Checked against the exact generic
+    kernel on the whole batch and against the oracle on both ends of it."""
+    ref, m = _pair(C, W, kind=kind)
+    _, mg = _pair(C, W, path="generic", kind=kind)
+    x = tskd_b200.synth.make_windows(B, C, W, "physio", seed=77, dtype=torch.bfloat16).to(DEV)
+    ages = tskd_b200.synth.make_ages(B, seed=77).to(DEV)
+    got = m.predict(x, ages)
+    assert m.last_path == "tensorcore"
+    exact = mg.predict(x, ages)
+    assert rel_err(got.cpu().numpy(), exact.cpu().numpy()) <= 2e-5
+    sel = torch.cat([torch.arange(0, 48), torch.arange(B - 48, B)])
+    want = O.ref_independent(ref, x[sel.to(DEV)].float().cpu(), ages[sel.to(DEV)].cpu()).numpy()
+    assert rel_err(got[sel.to(DEV)].cpu().numpy(), want) <= TOL
+    # the same windows in a small batch (one item per CTA at most): bit-identical
+    assert torch.equal(m.predict(x[:300], ages[:300]), got[:300])
+
+
 # ---- fp32 windows: streaming kernel (CUDA-core conv1 + tcgen05 projection), csrc/b2cnn_stream_f32.cuh ----
 
 @pytest.mark.parametrize("kind,C,W,B,dist", [

@@ -8,6 +8,11 @@
 //   head_sequence        one warp scans the batch axis carrying (h, c) -- the reference's
 //                        model(x_batch) semantics for B > 1 (models.py:29-30, utils.py:249)
 #include "b2cnn_internal.cuh"
+#include "b2cnn_head_dev.cuh"
+
+#ifndef B2CNN_HEAD_INFLIGHT
+#define B2CNN_HEAD_INFLIGHT 8                    // 16-byte loads of range partials in flight per lane
+#endif
 
 namespace b2cnn {
 
@@ -109,11 +114,7 @@ __global__ void reduce_gates_kernel(const float *__restrict__ part, int ksplit, 
 }
 
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float age_scale(float age, float coef) {
-    // models.py:32: relu(age * coef + 1) -- a separate multiply and add in the reference
-    float s = __fadd_rn(__fmul_rn(age, coef), 1.0f);
-    return (s > 0.f || s != s) ? s : 0.f;
-}
+__device__ __forceinline__ float age_scale(float age, float coef) { return head_age_scale(age, coef); }
 
 // One thread per window; zero initial state so W_hh * h and f * c vanish (kept as written).
 __global__ void __launch_bounds__(128)
@@ -161,75 +162,28 @@ head_independent_kernel(const float *__restrict__ gates0, HeadWeights hw, const 
 // Independent windows, reduction fused in: 16 lanes per window (lane u = hidden unit u), 16 windows per CTA.
 // gates0[b][g] = (sum_k partial[k][b][g] + b_ih[g]) + b_hh[g] in the same fixed order as reduce_gates_kernel
 // (windows a tensor-core front end flagged had their partial rows overwritten by the exact re-computation before
-// this kernel runs).  The arithmetic per window is that of head_independent_kernel, term for term.
+// this kernel runs).  The arithmetic per window is head_window16 (b2cnn_head_dev.cuh), which the fused streaming
+// kernel runs too; it equals head_independent_kernel term for term.
+// win_list / win_count (device memory, may be null): only the listed windows -- the exception path of the fused kernel.
 __global__ void __launch_bounds__(256)
 head_reduce_independent_kernel(const float *__restrict__ part, int slices, HeadWeights hw, const float *__restrict__ age,
-                               int64_t n_age, float coef, int apply_sigmoid, float *__restrict__ out, int64_t B) {
-    __shared__ float s_w1[kHidden][kGates];                // W_ih_l1 transposed: s_w1[k][row], conflict-free per k
-    for (int i = threadIdx.x; i < kGates * kHidden; i += blockDim.x) s_w1[i & 15][i >> 4] = __ldg(hw.wih1 + i);
-    const int lane = threadIdx.x & 31, u = lane & 15;
-    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    const bool live = b < B;
-    const int64_t bb = live ? b : B - 1;                   // dead lanes shadow the last window (shuffles stay full-warp)
-    float g4[4];
-    {
-        // lane u of the window's 16 lanes streams gates 4u .. 4u+3 of every slice with one 16-byte load (a window's
-        // row of a slice is one coalesced 256-byte read); every gate is still summed in slice order, so the result is
-        // bit-identical to reduce_gates_kernel.  Afterwards the sums are redistributed: unit u needs gates u, 16+u,
-        // 32+u, 48+u, which sit in lanes (q*16+u)/4 at component (q*16+u)%4 = u%4.
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 *row = reinterpret_cast<const float4 *>(part + bb * kGates) + u;
-        const int64_t slice_stride = B * (kGates / 4);
-        int k = 0;
-        for (; k + 8 <= slices; k += 8) {                  // 8 x 16-byte loads in flight per lane
-            float4 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(row + (int64_t)(k + j) * slice_stride);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
-        }
-        for (; k < slices; ++k) {
-            const float4 v = __ldg(row + (int64_t)k * slice_stride);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        const int base16 = lane & 16, comp = u & 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int src = base16 + ((q * kHidden + u) >> 2);
-            const float a = __shfl_sync(0xffffffffu, s.x, src), b2 = __shfl_sync(0xffffffffu, s.y, src);
-            const float c = __shfl_sync(0xffffffffu, s.z, src), d2 = __shfl_sync(0xffffffffu, s.w, src);
-            const float sum = comp == 0 ? a : comp == 1 ? b2 : comp == 2 ? c : d2;
-            g4[q] = (sum + __ldg(hw.bih0 + q * kHidden + u)) + __ldg(hw.bhh0 + q * kHidden + u);
-        }
-    }
-    __syncthreads();                                       // s_w1 complete
-    // layer 0 from the zero state
-    const float c0 = sigmoid_acc(g4[1]) * 0.f + sigmoid_acc(g4[0]) * tanhf(g4[2]);
-    const float h0 = sigmoid_acc(g4[3]) * tanhf(c0);
-    // layer 1: gi[q] = (sum_k W_ih_l1[q*16+u][k] h0[k] + b_ih) + b_hh, k ascending
-    float gi[4] = {0.f, 0.f, 0.f, 0.f};
-    const int base = lane & 16;
-#pragma unroll
-    for (int k = 0; k < kHidden; ++k) {
-        const float hk = __shfl_sync(0xffffffffu, h0, base + k);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) gi[q] = fmaf(s_w1[k][q * kHidden + u], hk, gi[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) gi[q] = (gi[q] + __ldg(hw.bih1 + q * kHidden + u)) + __ldg(hw.bhh1 + q * kHidden + u);
-    const float c1 = sigmoid_acc(gi[1]) * 0.f + sigmoid_acc(gi[0]) * tanhf(gi[2]);
-    const float h1 = sigmoid_acc(gi[3]) * tanhf(c1);
-    // Linear(16 -> 1): y = fma(wo[u], h1[u], y) for u ascending, exactly as the one-thread-per-window kernel
-    float y = 0.f;
-#pragma unroll
-    for (int k = 0; k < kHidden; ++k) {
-        const float hk = __shfl_sync(0xffffffffu, h1, base + k);
-        y = fmaf(__ldg(hw.wo + k), hk, y);
-    }
-    if (live && u == 0) {
-        y += __ldg(hw.bo);
-        y *= age_scale(age[n_age == 1 ? 0 : b], coef);
-        out[b] = apply_sigmoid ? sigmoid_acc(y) : y;
+                               int64_t n_age, float coef, int apply_sigmoid, float *__restrict__ out, int64_t B,
+                               const int *__restrict__ win_list, const int *__restrict__ win_count) {
+    __shared__ float s_w1[kHidden * kGates];               // W_ih_l1 transposed: s_w1[k * 64 + row], conflict-free per k
+    for (int i = threadIdx.x; i < kGates * kHidden; i += blockDim.x) s_w1[(i & 15) * kGates + (i >> 4)] = __ldg(hw.wih1 + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t nwin = win_count ? *win_count : B;
+    const int64_t per_pass = (int64_t)gridDim.x * (blockDim.x >> 4);
+    const int64_t passes = (nwin + per_pass - 1) / per_pass;                 // the same for every thread: shuffles stay full-warp
+    for (int64_t it = 0; it < passes; ++it) {
+        const int64_t wi = it * per_pass + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+        const bool live = wi < nwin;
+        const int64_t wl = live ? wi : nwin - 1;            // dead lanes shadow the last window
+        const int64_t b = win_list ? win_list[wl] : wl;
+        const float y = head_window16<true, B2CNN_HEAD_INFLIGHT>(reinterpret_cast<const float4 *>(part + b * kGates) + (lane & 15), B * (kGates / 4), slices, hw,
+                                            s_w1, age[n_age == 1 ? 0 : b], coef, apply_sigmoid, lane);
+        if (live && (lane & 15) == 0) out[b] = y;
     }
 }
 
@@ -338,7 +292,7 @@ int launch_reduce_gates(const float *partial, int slices, int64_t B, const HeadW
 int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, int64_t B,
                             const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err) {
     head_reduce_independent_kernel<<<(unsigned)((B * 16 + 255) / 256), 256, 0, st>>>(partial, slices, hw, age, n_age, d.age_coef,
-                                                                                  apply_sigmoid, out, B);
+                                                                                  apply_sigmoid, out, B, nullptr, nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     return 1;

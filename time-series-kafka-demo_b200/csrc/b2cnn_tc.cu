@@ -611,7 +611,12 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
     cudaError_t le = cudaSuccess;
     bool launched = false;
     {
-        dim3 grid((unsigned)((B + 2 * kTcM - 1) / (2 * kTcM)), s.n_ranges);
+        // persistent grid: one CTA per SM (218 KB of shared memory and all 512 TMEM columns each), static round-robin over
+        // the (window-tile pair, position range) items
+        const int64_t n_items = ((B + 2 * kTcM - 1) / (2 * kTcM)) * s.n_ranges;
+        if (n_items > 0x7fffffff) { *err = "batch too large for the fused kernel's item index"; return -1; }
+        p.n_ranges = s.n_ranges; p.n_items = (int)n_items;
+        dim3 grid((unsigned)(n_items < num_sms ? n_items : num_sms));
         const size_t smem = (size_t)4 * d.C * kTcABytes + (size_t)d.C * sp * kTcBBytes + 2 * kFuWChunkBytes + FuBars::kTotal * 8 + 16;
 #define FU_LAUNCH(CC, SS, AA)                                                                          \
         if (!launched && d.C == CC && sp == SS && arch_id == AA) {                                     \

@@ -19,6 +19,8 @@ struct TcState {
     int64_t opt_fused = 1;
 };
 
+
+
 const char *tc_error();
 int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_wih0, const HeadWeights &hw,
                int splits, int num_sms, cudaStream_t st);

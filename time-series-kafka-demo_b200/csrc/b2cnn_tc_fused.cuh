@@ -26,6 +26,7 @@
 #pragma once
 #include <type_traits>
 
+
 namespace b2cnn {
 
 // B2CNN_ABLATE (experiments only, see scripts/build_ablations.sh): 1 = epilogue without math (tensor/TMA-side
@@ -45,7 +46,7 @@ namespace b2cnn {
 #define B2CNN_SEGMENTS 0                          // 1 = a scheduling fence (pmevent) after every segment of the epilogue iteration (A/B: slower)
 #endif
 #ifndef B2CNN_LDTM_SEG
-#define B2CNN_LDTM_SEG -1                         // segment after which the next block's accumulators are requested (-1: top of the iteration)
+#define B2CNN_LDTM_SEG 8                          // segment after which the next block's accumulators are requested (-1: top of the iteration)
 #endif
 constexpr int kLdtmSeg = B2CNN_LDTM_SEG;
 #ifndef B2CNN_UNROLL8
@@ -71,6 +72,7 @@ struct TcFusedParams {
     const uint8_t *wpack;     // [n_ranges][chunks_per_cta][kFuWChunkBytes]
     int B, W, L;
     int tiles_per_cta, feats_per_cta, chunks_per_cta;
+    int n_ranges, n_items;    // work items = (pair of window tiles, position range), range fastest; CTA k runs items k, k + gridDim.x, ...
     // epilogue constants, paired over (out-)channels (2q, 2q+1) for the packed f32x2 arithmetic
     float2 w9p[kTcMaxC][2];    // tap k=9 of conv1: (w1[2q][c][9], w1[2q+1][c][9])
     float2 b1sp[2];            // conv1 bias * 2 log2 e
@@ -119,7 +121,7 @@ struct SegPlan {
 // barrier indices (uint64_t slots)
 struct FuBars {
     // per window tile t (stride kPerTile)
-    static constexpr int kFull = 0, kEmpty = 2, kTFull = 4, kTEmpty = 8, kPFull = 12, kPEmpty = 14, kGFull = 16, kPerTile = 17;
+    static constexpr int kFull = 0, kEmpty = 2, kTFull = 4, kTEmpty = 8, kPFull = 12, kPEmpty = 14, kGFull = 16, kGEmpty = 17, kPerTile = 18;
     static constexpr int kWFull = 2 * kPerTile, kWEmpty = kWFull + 2, kTotal = kWEmpty + 2;
 };
 
@@ -133,6 +135,8 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem[];
 #ifdef B2CNN_TIMING
     const long long t_entry = clock64();
+    unsigned long long gt_entry;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
 #endif
     // [2 tiles][2 stages][C][16 KB] | bands | W ring [2][6 KB] | barriers | tmem slot
     uint8_t *sA = smem;
@@ -145,15 +149,28 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
-    const int b_cta = blockIdx.x * 2 * kTcM;
-    const int p0 = blockIdx.y * p.feats_per_cta;
-    const int nfeat = min(p.feats_per_cta, p.L - p0);
     constexpr int FOFF = ARCH == 0 ? 3 : 2;           // step j emits features 2j-FOFF, 2j-FOFF+1
-    const int nsteps_needed = (nfeat + FOFF - 1) / 2 + 1;
-    const int ntiles = (nsteps_needed + kTcBlocks - 1) / kTcBlocks;
-    const int J = ntiles * kTcBlocks;                 // steps actually run
-    const int nchunks = (J + 7) / 8;
-    const int T0 = p0 * 4;
+    // Persistent CTA: one per SM, items k, k + gridDim.x, ... (static: every role walks the same list, nothing to
+    // exchange).  All pipelines run THROUGH the item boundaries -- the producer prefetches the next item's first tiles and
+    // the MMA warps start its conv1 blocks while the epilogue still drains the gates of the previous one -- so the per-CTA
+    // launch, TMEM allocation, band-matrix copy and pipeline fill are paid once per SM instead of once per item (measured
+    // with B2CNN_TIMING on the one-item-per-CTA kernel: 4.4 us from CTA entry to the first accumulators, and 16 % of the
+    // kernel's duration covered by no CTA at all: block-scheduler gaps between the waves).  Barrier phases carry over: every
+    // role counts tiles / chunks / ring uses globally.
+    struct Item { int r, b_cta, J, ntiles, nchunks, T0; };
+    auto item_geom = [&](int item) -> Item {
+        Item g;
+        g.r = item % p.n_ranges;
+        g.b_cta = (item / p.n_ranges) * 2 * kTcM;
+        const int p0 = g.r * p.feats_per_cta;
+        const int nfeat = min(p.feats_per_cta, p.L - p0);
+        const int nsteps_needed = (nfeat + FOFF - 1) / 2 + 1;
+        g.ntiles = (nsteps_needed + kTcBlocks - 1) / kTcBlocks;
+        g.J = g.ntiles * kTcBlocks;                   // steps actually run
+        g.nchunks = (g.J + 7) / 8;
+        g.T0 = p0 * 4;
+        return g;
+    };
 
     if ((smem_u32(smem) & 1023u) != 0) __trap();      // SWIZZLE_128B tiles need 1 KB alignment
     for (int i = threadIdx.x; i < C * SPLITS * kTcBBytes / 16; i += kFuThreads)
@@ -165,6 +182,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             for (int i = 0; i < 4; ++i) { mbar_init(BAR(o + FuBars::kTFull + i), 1); mbar_init(BAR(o + FuBars::kTEmpty + i), 4); }
             for (int i = 0; i < 2; ++i) { mbar_init(BAR(o + FuBars::kPFull + i), 4); mbar_init(BAR(o + FuBars::kPEmpty + i), 1); }
             mbar_init(BAR(o + FuBars::kGFull), 1);
+            mbar_init(BAR(o + FuBars::kGEmpty), 4);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(FuBars::kWFull + i), 1); mbar_init(BAR(FuBars::kWEmpty + i), 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -187,15 +205,19 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #ifdef B2CNN_TIMING
             const long long tp0 = clock64();
 #endif
-            for (int i = 0; i < ntiles; ++i) {
-                const int s = i & 1, ph = (i >> 1) & 1;
-                for (int t = 0; t < 2; ++t) {
-                    const int o = t * FuBars::kPerTile;
-                    { FU_T0(); mbar_wait_parked(BAR(o + FuBars::kEmpty + s), ph ^ 1); FU_TACC(9, true); }
-                    mbar_expect_tx(BAR(o + FuBars::kFull + s), C * kTcABytes);
+            int gi = 0;                                     // tiles requested so far (all items): stage = gi & 1
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const Item g = item_geom(item);
+                for (int i = 0; i < g.ntiles; ++i, ++gi) {
+                    const int s = gi & 1, ph = (gi >> 1) & 1;
+                    for (int t = 0; t < 2; ++t) {
+                        const int o = t * FuBars::kPerTile;
+                        { FU_T0(); mbar_wait_parked(BAR(o + FuBars::kEmpty + s), ph ^ 1); FU_TACC(9, true); }
+                        mbar_expect_tx(BAR(o + FuBars::kFull + s), C * kTcABytes);
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        tma_load_3d(smem_u32(sA_of(t, s, c)), &tmap, T0 + kTcAdv * i, c, b_cta + t * kTcM, BAR(o + FuBars::kFull + s));
+                        for (int c = 0; c < C; ++c)
+                            tma_load_3d(smem_u32(sA_of(t, s, c)), &tmap, g.T0 + kTcAdv * i, c, g.b_cta + t * kTcM, BAR(o + FuBars::kFull + s));
+                    }
                 }
             }
 #ifdef B2CNN_TIMING
@@ -217,11 +239,15 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const uint32_t b_lo0 = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
         const uint32_t w_lo0 = (uint32_t)w_base, w_hi = (uint32_t)(w_base >> 32);
         const uint32_t tcol = tmem_base + t * 256;
-        auto issue_proj = [&](int m) {
-            const int u = m & 1, ph = (m >> 1) & 1;
+        int gi = 0, gm = 0, it = 0;                         // tiles, chunks, items done so far
+        uint32_t rpar = 0;                                  // bit s: parity of the number of uses of accumulator-ring slot s
+        // m: chunk of the current item, gmm: its global number (A buffer / W stage = gmm & 1)
+        auto issue_proj = [&](int m, int gmm) {
+            const int u = gmm & 1, ph = (gmm >> 1) & 1;
             { FU_T0();
             mbar_wait_parked(BAR(FuBars::kWFull + u), ph);
             mbar_wait_parked(BAR(o + FuBars::kPFull + u), ph);
+            if (m == 0) mbar_wait_parked(BAR(o + FuBars::kGEmpty), (it & 1) ^ 1);   // the previous item's gates left TMEM
             FU_TACC(7, lane == 0); }
             tc_fence_after();
             if (elect_one()) {
@@ -240,20 +266,24 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             }
             __syncwarp();
         };
-        int m_done = 0, n = 0, i = 0;
 #ifdef B2CNN_TIMING
         const long long tm0 = clock64();
 #endif
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item g = item_geom(item);
+        const int J = g.J, nchunks = g.nchunks;
+        int m_done = 0, n = 0;
         for (int j = 0; j < J; ++j) {
-            const int s = i & 1, slot = j & 3;
-            if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done); ++m_done; }
+            const int s = gi & 1, slot = j & 3;              // ring slots restart with every item, their phases do not
+            if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done, gm + m_done); ++m_done; }
 #if B2CNN_MMA_SPIN
-            if (n == 0) mbar_wait(BAR(o + FuBars::kFull + s), (i >> 1) & 1);
-            mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1);
+            if (n == 0) mbar_wait(BAR(o + FuBars::kFull + s), (gi >> 1) & 1);
+            mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((rpar >> slot) & 1) ^ 1);
 #else
-            { FU_T0(); if (n == 0) mbar_wait_parked(BAR(o + FuBars::kFull + s), (i >> 1) & 1); FU_TACC(5, lane == 0); }
-            { FU_T0(); mbar_wait_parked(BAR(o + FuBars::kTEmpty + slot), ((j >> 2) & 1) ^ 1); FU_TACC(6, lane == 0); }
+            { FU_T0(); if (n == 0) mbar_wait_parked(BAR(o + FuBars::kFull + s), (gi >> 1) & 1); FU_TACC(5, lane == 0); }
+            { FU_T0(); mbar_wait_parked(BAR(o + FuBars::kTEmpty + slot), ((rpar >> slot) & 1) ^ 1); FU_TACC(6, lane == 0); }
 #endif
+            rpar ^= 1u << slot;
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t d = tcol + slot * 32;
@@ -275,27 +305,33 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 umma_commit(BAR(o + FuBars::kTFull + slot));
             }
             __syncwarp();
-            if (++n == kTcBlocks) { n = 0; ++i; }
+            if (++n == kTcBlocks) { n = 0; ++gi; }
         }
-        for (; m_done < nchunks; ++m_done) issue_proj(m_done);
+        for (; m_done < nchunks; ++m_done) issue_proj(m_done, gm + m_done);
+        if (elect_one()) umma_commit(BAR(o + FuBars::kGFull));
+        __syncwarp();
+        gm += nchunks; ++it;
+        }
 #ifdef B2CNN_TIMING
         if (lane == 0) atomicAdd(&g_fu_timing[4], (unsigned long long)(clock64() - tm0));
 #endif
         FU_TFLUSH(4, lane == 0);
-        if (elect_one()) umma_commit(BAR(o + FuBars::kGFull));
-        __syncwarp();
     } else if (warp == 3) {
         // ===================== W_ih chunk producer (and TMEM allocator) =====================
         // Separate from the window-tile producer: a chunk may only be refilled after BOTH window
         // tiles projected the chunk two back, and that wait must never delay the next A-tile request.
         if (lane == 0) {
-            const uint8_t *wsrc = p.wpack + (size_t)blockIdx.y * p.chunks_per_cta * kFuWChunkBytes;
-            for (int m = 0; m < nchunks; ++m) {
-                const int u = m & 1;
-                mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((m >> 1) & 1) ^ 1);
-                mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
-                bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m * kFuWChunkBytes, kFuWChunkBytes,
-                             BAR(FuBars::kWFull + u));
+            int gm = 0;                                     // chunks requested so far (all items): stage = gm & 1
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const Item g = item_geom(item);
+                const uint8_t *wsrc = p.wpack + (size_t)g.r * p.chunks_per_cta * kFuWChunkBytes;
+                for (int m = 0; m < g.nchunks; ++m, ++gm) {
+                    const int u = gm & 1;
+                    mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((gm >> 1) & 1) ^ 1);
+                    mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
+                    bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m * kFuWChunkBytes, kFuWChunkBytes,
+                                 BAR(FuBars::kWFull + u));
+                }
             }
         }
     } else {
@@ -311,31 +347,21 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const int o_bar = t * FuBars::kPerTile;
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int b = b_cta + t * kTcM + row;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
         const uint32_t swz = (uint32_t)(row & 7);
-        const bool row_ok = b < p.B;
         FU_TDECL();
+        int J = 0;                                          // steps of the current item
+        int gmb = 0, it = 0;                                // chunks / items finished so far (A buffer = global chunk & 1)
+        uint32_t tqm = 0, tq[4] = {0, 0, 0, 0};             // parity of the uses of accumulator-ring slot s in the items before (mask, and per slot)
         // a1 history: abuf[jj & 1] holds the 4 activations x 4 channels produced by stage A of block jj
         // all per-channel state is held as float2 over channel pairs (0,1) and (2,3)
         float2 pm6[2], pm7[2], abuf[2][4][2];
         float c2s[2][4];                                    // conv2 outputs: Bc of iteration jj writes c2s[jj & 1], Bt of jj + 1 reads them
         float c2c = 0.f;
-#pragma unroll
-        for (int q2 = 0; q2 < 2; ++q2) {
-            pm6[q2] = make_float2(0.f, 0.f); pm7[q2] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { abuf[0][i][q2] = make_float2(0.f, 0.f); abuf[1][i][q2] = make_float2(0.f, 0.f); }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { c2s[0][i] = 0.f; c2s[1][i] = 0.f; }
         // accumulator registers are double-buffered by step parity (block jj lives in Dbuf[jj & 1]; the
         // next block's tcgen05.ld is issued into the other half) -- no register-to-register copies
         uint32_t Dbuf[2][32];
-        mbar_wait_parked(BAR(o_bar + FuBars::kTFull + 0), 0);
-        tc_fence_after();
-        tmem_ld32_issue(tlane + 0, Dbuf[0]);
-        int n = 0, ti = 0;                                  // block-in-tile and tile index of block jj
+        int n = 0, ti = 0;                                  // block-in-tile of block jj; tiles consumed so far (all items)
         float2 w2r[2][5];                                   // conv2 weights stay in registers for the whole stream
 #pragma unroll
         for (int q2 = 0; q2 < 2; ++q2)
@@ -360,13 +386,14 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             // the next block's accumulators -> the other half of Dbuf (dead since the previous iteration copied its carries out).
             // kLdtmSeg < 0: at the top of the iteration; else after that segment of the math: the later it is asked for,
             // the more slack the MMA warp has to refill the ring, as long as the load still lands before the next iteration
+            const uint32_t tqs = KK >= 0 ? tq[KK >= 0 ? ((KK + 2) & 3) : 0] : ((tqm >> slot1) & 1u);
             auto prefetch_next = [&]() {
                 if (KK >= 0 || jj + 1 < J) {
                     FU_T0();
 #if B2CNN_EPI_SPIN
-                    mbar_wait(BAR(o_bar + FuBars::kTFull + slot1), par1);
+                    mbar_wait(BAR(o_bar + FuBars::kTFull + slot1), par1 ^ tqs);
 #else
-                    mbar_wait_parked(BAR(o_bar + FuBars::kTFull + slot1), par1);
+                    mbar_wait_parked(BAR(o_bar + FuBars::kTFull + slot1), par1 ^ tqs);
 #endif
                     FU_TACC(1, lane == 0);
                     tc_fence_after();
@@ -394,6 +421,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             float2 an[4][2];
             const uint32_t acol = tlane + 128 + u * 24 + kk;
 #if B2CNN_ABLATE == 1
+            if constexpr (doA && kLdtmSeg >= 0) prefetch_next();
             if constexpr (doA) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -567,12 +595,32 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         using P0 = std::integral_constant<int, 0>;
         using P1 = std::integral_constant<int, 1>;
         using KR = std::integral_constant<int, -1>;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item g = item_geom(item);
+        J = g.J;
+        const int b = g.b_cta + t * kTcM + row;
+        const bool row_ok = b < p.B;
+        // stream state of a new item: everything it emits before its own data arrives is multiplied by zero weights, but
+        // a NaN left over from the previous item's windows must not leak into this one's (0 * NaN = NaN would flag them)
+        c2c = 0.f;
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+            pm6[q2] = make_float2(0.f, 0.f); pm7[q2] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { abuf[0][i][q2] = make_float2(0.f, 0.f); abuf[1][i][q2] = make_float2(0.f, 0.f); }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { c2s[0][i] = 0.f; c2s[1][i] = 0.f; }
+        n = 0;
+        mbar_wait_parked(BAR(o_bar + FuBars::kTFull + 0), tq[0]);
+        tc_fence_after();
+        tmem_ld32_issue(tlane + 0, Dbuf[0]);
 #ifdef B2CNN_TIMING
         const long long te0 = clock64();
-        if (lane == 0) atomicAdd(&g_fu_timing[12], (unsigned long long)(te0 - t_entry));
+        if (lane == 0 && item == (int)blockIdx.x) atomicAdd(&g_fu_timing[12], (unsigned long long)(te0 - t_entry));
 #endif
-        iteration(0, 0, T_{}, F_{}, F_{}, P0{}, KR{});
-        iteration(1, 0, T_{}, T_{}, F_{}, P1{}, KR{});     // J is a multiple of kTcBlocks = 7: blocks 0 and 1 always exist
+        iteration(0, gmb, T_{}, F_{}, F_{}, P0{}, KR{});
+        iteration(1, gmb, T_{}, T_{}, F_{}, P1{}, KR{});   // J is a multiple of kTcBlocks = 7: blocks 0 and 1 always exist
         int jj = 2;
 #if B2CNN_UNROLL8
         // whole chunks whose every iteration has a successor block (jj + 1 < J): iterations 8c+2 .. 8c+9 store the features
@@ -580,40 +628,41 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const int nfull = J >= 11 ? (J - 3) >> 3 : 0;
 #pragma unroll 1
         for (int c = 0; c < nfull; ++c, jj += 8) {
-            iteration(jj + 0, c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 1>{});
-            iteration(jj + 1, c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 2>{});
-            iteration(jj + 2, c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 3>{});
-            iteration(jj + 3, c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 4>{});
-            iteration(jj + 4, c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 5>{});
-            iteration(jj + 5, c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 6>{});
-            iteration(jj + 6, c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 7>{});
-            iteration(jj + 7, c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 0>{});
+            iteration(jj + 0, gmb + c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 1>{});
+            iteration(jj + 1, gmb + c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 2>{});
+            iteration(jj + 2, gmb + c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 3>{});
+            iteration(jj + 3, gmb + c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 4>{});
+            iteration(jj + 4, gmb + c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 5>{});
+            iteration(jj + 5, gmb + c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 6>{});
+            iteration(jj + 6, gmb + c, T_{}, T_{}, T_{}, P0{}, std::integral_constant<int, 7>{});
+            iteration(jj + 7, gmb + c, T_{}, T_{}, T_{}, P1{}, std::integral_constant<int, 0>{});
         }
 #endif
 #pragma unroll 1
         for (; jj + 1 < J; jj += 2) {                       // two iterations per trip: register names alternate (jj is even here)
-            iteration(jj, (jj - 2) >> 3, T_{}, T_{}, T_{}, P0{}, KR{});
-            iteration(jj + 1, (jj - 1) >> 3, T_{}, T_{}, T_{}, P1{}, KR{});
+            iteration(jj, gmb + ((jj - 2) >> 3), T_{}, T_{}, T_{}, P0{}, KR{});
+            iteration(jj + 1, gmb + ((jj - 1) >> 3), T_{}, T_{}, T_{}, P1{}, KR{});
         }
-        if (jj < J) { iteration(jj, (jj - 2) >> 3, T_{}, T_{}, T_{}, P0{}, KR{}); ++jj; }
+        if (jj < J) { iteration(jj, gmb + ((jj - 2) >> 3), T_{}, T_{}, T_{}, P0{}, KR{}); ++jj; }
         // jj == J: drain the pipeline (conv2 of step J-1, features of steps J-2 and J-1)
         if (J & 1) {
-            iteration(J, (J - 2) >> 3, F_{}, T_{}, T_{}, P1{}, KR{});
-            iteration(J + 1, (J - 1) >> 3, F_{}, F_{}, T_{}, P0{}, KR{});
+            iteration(J, gmb + ((J - 2) >> 3), F_{}, T_{}, T_{}, P1{}, KR{});
+            iteration(J + 1, gmb + ((J - 1) >> 3), F_{}, F_{}, T_{}, P0{}, KR{});
         } else {
-            iteration(J, (J - 2) >> 3, F_{}, T_{}, T_{}, P0{}, KR{});
-            iteration(J + 1, (J - 1) >> 3, F_{}, F_{}, T_{}, P1{}, KR{});
+            iteration(J, gmb + ((J - 2) >> 3), F_{}, T_{}, T_{}, P0{}, KR{});
+            iteration(J + 1, gmb + ((J - 1) >> 3), F_{}, F_{}, T_{}, P1{}, KR{});
         }
 
 #ifdef B2CNN_TIMING
         if (lane == 0) atomicAdd(&g_fu_timing[0], (unsigned long long)(clock64() - te0));
         const long long tg0 = clock64();
-#endif
         FU_TFLUSH(0, lane == 0);
+        for (int i__ = 0; i__ < 4; ++i__) fu_tacc[i__] = 0;
+#endif
         // ---- gate pre-activations of this CTA's position range -> partial[range][window][64]
-        mbar_wait_parked(BAR(o_bar + FuBars::kGFull), 0);
+        mbar_wait_parked(BAR(o_bar + FuBars::kGFull), it & 1);
         tc_fence_after();
-        float *dst = p.partial + ((int64_t)blockIdx.y * p.B + b) * kGates;
+        float *dst = p.partial + ((int64_t)g.r * p.B + b) * kGates;
         // A NaN feature (a NaN / inf sample met a zero of the band matrix, or a real NaN) makes every gate it is
         // multiplied into NaN -- zero weights included -- so the 64 sums themselves are the probe: no per-step test.
         bool bad = false;
@@ -632,9 +681,26 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
         // up to n_ranges CTAs may flag the same window: the first one appends it to the list of the exact re-computation
         if (row_ok && bad && atomicExch(&p.nanflag[b], 1) == 0) p.list[atomicAdd(p.count, 1)] = b;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(o_bar + FuBars::kGEmpty));          // the MMA warp may start the next item's gate sums
+        // phases of the next item: ring slot s was used ceil((J - s) / 4) times, the chunk counter moves on
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) tq[sl] ^= (uint32_t)((J - sl + 3) >> 2) & 1u;
+        tqm = tq[0] | (tq[1] << 1) | (tq[2] << 2) | (tq[3] << 3);
+        gmb += g.nchunks; ++it;
 #ifdef B2CNN_TIMING
         if (lane == 0) atomicAdd(&g_fu_timing[10], (unsigned long long)(clock64() - tg0));
-        if (threadIdx.x == 128 && blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&g_fu_timing[11], 1ull);
+#endif
+        }   // items
+#ifdef B2CNN_TIMING
+        if (threadIdx.x == 128 && blockIdx.x == 0) {
+            atomicAdd(&g_fu_timing[11], 1ull);
+            unsigned long long gt_exit;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_exit));
+            atomicAdd(&g_fu_timing[14], gt_exit - gt_entry);                                  // ns
+            atomicAdd(&g_fu_timing[15], (unsigned long long)(clock64() - t_entry));          // SM cycles over the same span
+        }
         if (lane == 0) atomicAdd(&g_fu_timing[13], (unsigned long long)(clock64() - t_entry));
 #endif
     }
