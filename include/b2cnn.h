@@ -230,6 +230,30 @@ int b2cnn_frame_check(const void *frame, int64_t bytes, b2cnn_frame_header *head
 const char *b2cnn_last_error(void);
 const char *b2cnn_version(void);
 
+/* ---- One training step on the device ----
+ * Replaces the body of the reference's training loop (bin/utils.py:200-208):
+ *     optimizer.zero_grad(); output = model(input, age); loss = criterion(output, target); loss.backward(); optimizer.step()
+ * with criterion = nn.BCEWithLogitsLoss() (bin/utils.py:663) and torch.optim.Adam (bin/explore_torch.ipynb:3204-3205;
+ * no amsgrad, no weight decay), for the model in train() mode: B2CNN_MODE_SEQUENCE is what model(input_batch, age)
+ * computes (the LSTM scans the batch axis, bin/models.py:29-30), B2CNN_MODE_INDEPENDENT treats every window as its own
+ * sequence.  All pointers are DEVICE pointers, everything is fp32:
+ *   params          the packed blob of b2cnn_weight_count() floats (no affine), updated in place when apply_update != 0
+ *   adam_m, adam_v  optimizer state, same size (zero before step 1); grads: same size, receives d loss / d params
+ *   step            1-based count of optimizer steps (bias correction)
+ *   x [B][C][W], age [B], target [B] (0 / 1)
+ *   mask1 [B][4][P1], mask2 [B][L_out]: the two nn.Dropout(0.1) masks of bin/models.py:25,28 ALREADY scaled by 1/(1-p)
+ *                   (torch's Philox stream cannot be reproduced here, so the caller draws them); NULL = no dropout
+ *   loss_out        one float: the mean BCE-with-logits loss of this batch (before the update)
+ * The call allocates nothing and is asynchronous on `stream`. */
+typedef struct b2cnn_adam {
+    float lr, beta1, beta2, eps;   /* torch defaults: 1e-3, 0.9, 0.999, 1e-8 */
+} b2cnn_adam;
+int64_t b2cnn_train_workspace_bytes(const b2cnn_config *cfg, int64_t B);
+int b2cnn_train_step(const b2cnn_config *cfg, float *params, float *adam_m, float *adam_v, float *grads, int64_t step,
+                     const b2cnn_adam *opt, int apply_update, const float *x, int64_t B, const float *age, const float *target,
+                     int mode, const float *mask1, const float *mask2, float *loss_out, void *workspace, int64_t workspace_bytes,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

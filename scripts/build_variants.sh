@@ -8,7 +8,7 @@ for spec in "$@"; do
   name=${spec%%:*}; flags=${spec#*:}
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -cudart shared \
     $flags -o time-series-kafka-demo_b200/lib/libb2cnn_$name.so \
-    $CS/b2cnn_api.cu $CS/b2cnn_generic.cu $CS/b2cnn_head.cu $CS/b2cnn_small.cu $CS/b2cnn_batch.cu $CS/b2cnn_prep.cu $CS/b2cnn_wire.cu $CS/b2cnn_tc.cu &
+    $CS/b2cnn_api.cu $CS/b2cnn_generic.cu $CS/b2cnn_head.cu $CS/b2cnn_small.cu $CS/b2cnn_batch.cu $CS/b2cnn_prep.cu $CS/b2cnn_wire.cu $CS/b2cnn_train.cu $CS/b2cnn_tc.cu &
 done
 wait
 ls time-series-kafka-demo_b200/lib/

@@ -166,3 +166,20 @@ def test_synth_is_deterministic():
     assert torch.isnan(e[0]).any() and torch.isinf(e[1]).any()
     ages = tskd_b200.synth.make_ages(100)
     assert ages.min() >= 15 and ages.max() <= 80
+
+
+def test_train_entry_points_validate_without_a_gpu():
+    """b2cnn_train_workspace_bytes is pure host arithmetic; b2cnn_train_step rejects bad arguments before touching CUDA."""
+    import ctypes
+    from tskd_b200 import capi
+    lib = capi.load_library()
+    cfg = capi.make_config(tskd_b200.ARCH_PRESETS["mycnn5"])
+    n = lib.b2cnn_train_workspace_bytes(ctypes.byref(cfg), 32)
+    assert n > 32 * (4 * 111 + 4 * 55 + 51 + 25) * 4
+    bad = capi.make_config(tskd_b200.ARCH_PRESETS["mycnn5"].with_shape(10, 121))    # L_out(121) == 25 still; break the view instead
+    bad.lstm_input = 24
+    assert lib.b2cnn_train_workspace_bytes(ctypes.byref(bad), 32) < 0
+    opt = capi.Adam(1e-3, 0.9, 0.999, 1e-8)
+    rc = lib.b2cnn_train_step(ctypes.byref(cfg), None, None, None, None, 1, ctypes.byref(opt), 1, None, 4, None, None, 1, None, None,
+                              None, None, 0, None)
+    assert rc == capi.EINVAL and "null" in capi.last_error()

@@ -112,6 +112,30 @@ extern "C" int64_t b2cnn_weight_count(const b2cnn_config *cfg) {
 
 extern "C" const char *b2cnn_last_error(void) { return g_err.c_str(); }
 
+// ---- one training step (b2cnn_train.cu) ----
+extern "C" int64_t b2cnn_train_workspace_bytes(const b2cnn_config *cfg, int64_t B) {
+    const int64_t n = train_workspace_bytes(cfg, B);
+    if (n < 0) fail(B2CNN_EINVAL, "b2cnn_train_workspace_bytes: bad configuration / batch");
+    return n;
+}
+extern "C" int b2cnn_train_step(const b2cnn_config *cfg, float *params, float *adam_m, float *adam_v, float *grads, int64_t step,
+                                const b2cnn_adam *opt, int apply_update, const float *x, int64_t B, const float *age,
+                                const float *target, int mode, const float *mask1, const float *mask2, float *loss_out,
+                                void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!cfg || !opt) return fail(B2CNN_EINVAL, "b2cnn_train_step: null configuration");
+    if (mode != B2CNN_MODE_INDEPENDENT && mode != B2CNN_MODE_SEQUENCE) return fail(B2CNN_EINVAL, "b2cnn_train_step: bad mode");
+    int prev = -1;
+    if (cfg->device >= 0) {
+        if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(cfg->device) != cudaSuccess) return fail(B2CNN_ECUDA, "b2cnn_train_step: cudaSetDevice");
+    }
+    const char *err = "";
+    const int rc = train_step(cfg, params, adam_m, adam_v, grads, step, opt->lr, opt->beta1, opt->beta2, opt->eps, apply_update, x, B, age,
+                              target, mode == B2CNN_MODE_SEQUENCE ? 1 : 0, mask1, mask2, loss_out, workspace, workspace_bytes,
+                              reinterpret_cast<cudaStream_t>(stream), &err);
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc == B2CNN_OK ? rc : fail(rc, std::string("b2cnn_train_step: ") + err);
+}
+
 // ---- preprocessing + window assembly (b2cnn_prep.cu) ----
 extern "C" int64_t b2cnn_prep_window_count(int64_t n_samples, double fs, const b2cnn_prep_config *cfg) {
     const int64_t n = prep_window_count(n_samples, fs, cfg);

@@ -154,6 +154,13 @@ int wire_decode_arrays(const uint8_t *bytes, const int64_t *offsets, int64_t n_m
                        int *n_bad, cudaStream_t st, const char **err);
 double wire_parse_decimal_host(const char *s, int64_t len, int *status);
 
+// b2cnn_train.cu: one training step (row f4)
+int64_t train_workspace_bytes(const b2cnn_config *cfg, int64_t B);
+int train_step(const b2cnn_config *cfg, float *params, float *adam_m, float *adam_v, float *grads, int64_t step, float lr, float beta1,
+               float beta2, float eps, int apply_update, const float *x, int64_t B, const float *age, const float *target, int sequence,
+               const float *mask1, const float *mask2, float *loss_out, void *workspace, int64_t ws_bytes, cudaStream_t st,
+               const char **err);
+
 void launch_transpose_wih(const float *wih0, float *wih0T, int L, cudaStream_t st);
 
 }  // namespace b2cnn

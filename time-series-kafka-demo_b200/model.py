@@ -85,8 +85,8 @@ class B200MyCNN(nn.Module):
 
     def train(self, mode: bool = True):
         if mode:
-            raise NotImplementedError("B200MyCNN is inference-only; the training step is out of "
-                                      "scope for this path (SURVEY.md section 8 f4)")
+            raise NotImplementedError("B200MyCNN.forward is the inference path (no dropout); the reference's training-loop "
+                                      "body (bin/utils.py:200-208) is B200Trainer(model).step(x, age, target)")
         return super().train(False)
 
     # ------------------------------------------------------------------ library plumbing
