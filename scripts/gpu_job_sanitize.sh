@@ -23,6 +23,22 @@ for kind in ("mycnn5", "mycnn3"):
         err = float(np.max(np.abs(y.cpu().numpy() - want) / np.maximum(np.abs(want), 1e-6)))
         print(kind, dt, m.last_path, "rel", err)
         ys = m(x[:5], a[:5]); torch.cuda.synchronize()
+# persistent grid: more (window-tile pair, range) items than SMs, several items per CTA
+oarch = O.stretched(O.ARCHS["mycnn5"], 3, 1528)
+ref = O.make_ref(oarch, seed=0)
+arch = replace(tskd_b200.ARCH_PRESETS["mycnn5"].with_shape(3, 1528), age_coef=oarch.age_coef)
+m = tskd_b200.B200MyCNN(arch, has_out12=oarch.has_out12, path="tensorcore").to("cuda:0"); m.load_state_dict(ref.state_dict())
+x = tskd_b200.synth.make_windows(2600, 3, 1528, "physio", seed=4, dtype=torch.bfloat16).to("cuda:0")
+a = tskd_b200.synth.make_ages(2600, seed=4).to("cuda:0")
+y = m.predict(x, a); torch.cuda.synchronize()
+want = O.ref_independent(ref, x[:64].float().cpu(), a[:64].cpu()).numpy()
+print("persistent", m.last_path, "rel", float(np.max(np.abs(y[:64].cpu().numpy() - want) / np.maximum(np.abs(want), 1e-6))))
+# one training step (row f4)
+from tskd_b200.trainer import B200Trainer
+mt = tskd_b200.B200MyCNN(tskd_b200.ARCH_PRESETS["mycnn5"]).to("cuda:0")
+tr = B200Trainer(mt, dropout=0.1)
+xt = torch.randn(24, 10, 120, device="cuda:0"); at = torch.full((24,), 60.0, device="cuda:0"); yt = (torch.rand(24, device="cuda:0") > 0.5).float()
+print("train loss", float(tr.step(xt, at, yt)), float(tr.step(xt, at, yt)))
 from conftest import load_golden
 gd, _ = load_golden("p000194_replay.npz")
 rec = S.NumericsRecord(tuple(str(n) for n in gd["names"]), gd["gains"], gd["baselines"], float(gd["fs"]), gd["raw"])
