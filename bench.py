@@ -538,7 +538,7 @@ def main():
                "roofline": roof, "parity": parity, "clocks": clocks, "sustained": sustained,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes,
                        "d2h_bytes_per_step": Be * 4, "steps": args.e2e_steps, "note": "per GPU; pinned host tensors through predict()",
-                       "pcie": {"h2d_peak_gbs": h2d_gbs, "achieved_gbs": e2e_gbs / world, "frac": e2e_gbs / world / h2d_gbs,
+                       "pcie": {"h2d_peak_gbs": h2d_gbs, "achieved_gbs": e2e_gbs, "frac": e2e_gbs / h2d_gbs,      # per GPU: every rank moves its own shard over its own link
                                 "peak_source": "pinned cudaMemcpyAsync H2D of the same buffer, same run (CUDA events)"}},
                "gpu_launches": launches_per_step * args.steps}
         if world == 1 and not args.no_cpu_baseline:
@@ -558,7 +558,7 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # committed ncu captures under profiles/ (None until a capture exists for that path).
 TRAFFIC = {"generic": 1.846642e9 + 0.297926e9,      # profiles/r01_generic_frontend_ncu_full.txt (features written to HBM)
-           "tensorcore": 1.944850e9 + 0.034090e9,   # profiles/r01_final_fused_ncu_full.txt (halo re-reads + gate partials)
+           "tensorcore": 1.974306e9 + 0.034638e9,   # profiles/r02_persist_fused_ncu_full.txt (halo re-reads + gate partials)
            "stream": 3.801502e9 + 0.034493e9}       # profiles/r01_final_stream_ncu_full.txt (fp32 windows)
 
 if __name__ == "__main__":
