@@ -49,6 +49,9 @@ namespace b2cnn {
 #define B2CNN_LDTM_SEG 8                          // segment after which the next block's accumulators are requested (-1: top of the iteration)
 #endif
 constexpr int kLdtmSeg = B2CNN_LDTM_SEG;
+#ifndef B2CNN_PARTIAL_EVICT_LAST
+#define B2CNN_PARTIAL_EVICT_LAST 0                // experiment: range partials stored with an L2 evict-last hint (A/B: head 18.5 -> 16.3 us, kernel +6 us: no gain)
+#endif
 #ifndef B2CNN_UNROLL8
 #define B2CNN_UNROLL8 1                           // epilogue main loop unrolled over one 8-step projection chunk (compile-time indices)
 #endif
@@ -663,6 +666,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         mbar_wait_parked(BAR(o_bar + FuBars::kGFull), it & 1);
         tc_fence_after();
         float *dst = p.partial + ((int64_t)g.r * p.B + b) * kGates;
+#if B2CNN_PARTIAL_EVICT_LAST
+        uint64_t pol_last;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+#endif
         // A NaN feature (a NaN / inf sample met a zero of the band matrix, or a real NaN) makes every gate it is
         // multiplied into NaN -- zero weights included -- so the 64 sums themselves are the probe: no per-step test.
         bool bad = false;
@@ -675,8 +682,15 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             for (int k = 0; k < 32; ++k) bad |= (G[k] & 0x7fffffffu) > 0x7f800000u;
             if (row_ok) {
 #pragma unroll
-                for (int k = 0; k < 32; k += 4)
+                for (int k = 0; k < 32; k += 4) {
+#if B2CNN_PARTIAL_EVICT_LAST
+                    // the head reads these 39 MB back right after the kernel: ask the L2 to keep them while 1.8 GB of windows stream through
+                    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst + half * 32 + k), "r"(G[k]), "r"(G[k + 1]),
+                                 "r"(G[k + 2]), "r"(G[k + 3]), "l"(pol_last) : "memory");
+#else
                     *reinterpret_cast<uint4 *>(dst + half * 32 + k) = make_uint4(G[k], G[k + 1], G[k + 2], G[k + 3]);
+#endif
+                }
             }
         }
         // up to n_ranges CTAs may flag the same window: the first one appends it to the list of the exact re-computation
