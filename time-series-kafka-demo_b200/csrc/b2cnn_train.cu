@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(64)
 train_lstm_fwd(const float *__restrict__ f, const float *__restrict__ prm, BlobOff o, TrainDims d, int64_t B, int sequence,
                const float *__restrict__ age, const float *__restrict__ target, float *__restrict__ acts, float *__restrict__ cs,
                float *__restrict__ hs, float *__restrict__ z, float *__restrict__ loss_out) {
-    __shared__ float g[kGates], h0[kHidden], c0[kHidden], h1[kHidden], c1s[kHidden], red[kGates];
+    __shared__ float g[kGates], h0[kHidden], c0[kHidden], h1[kHidden], c1s[kHidden];
     const int r = threadIdx.x;
     if (r < kHidden) { h0[r] = c0[r] = h1[r] = c1s[r] = 0.f; }
     float loss = 0.f;
@@ -207,7 +207,6 @@ train_lstm_fwd(const float *__restrict__ f, const float *__restrict__ prm, BlobO
         __syncthreads();
     }
     if (r == 0) *loss_out = loss / (float)B;
-    (void)red;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
