@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 L=$PWD/time-series-kafka-demo_b200/lib
 for name in base ${VARIANTS}; do
   if [ $name = base ]; then lib=$L/libb2cnn.so; else lib=$L/libb2cnn_$name.so; fi
-  B2CNN_LIB=$lib timeout -k 10 120 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 1 --sustained-seconds 2.5 --parity-windows 0 ${EXTRA} > gpurun_out/pw_$name.json 2>> gpurun_out/pw.err
+  B2CNN_LIB=$lib timeout -k 10 120 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 1 --sustained-seconds 2.5 --parity-windows 0 --extra-steps 0 ${EXTRA} > gpurun_out/pw_$name.json 2>> gpurun_out/pw.err
   python - <<PY
 import json
 d = json.loads(open("gpurun_out/pw_$name.json").read().strip().splitlines()[-1])
