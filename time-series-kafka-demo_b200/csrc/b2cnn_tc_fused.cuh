@@ -61,10 +61,6 @@ constexpr int kFuWChunkBytes = 3 * 64 * 16 * 2;   // 3 pieces x (64 gates x 16 p
 #define B2CNN_COLLECTOR 1
 #endif
 constexpr bool kFuCollector = B2CNN_COLLECTOR != 0;   // A-operand collector reuse across the piece-MMAs of a (block, channel)
-#ifndef B2CNN_FULAG
-#define B2CNN_FULAG 4                             // A/B-timed: 2 -> +4 %, 6 -> +0.4 % kernel time
-#endif
-constexpr int kFuLag = B2CNN_FULAG;                         // conv1 blocks the MMA thread runs ahead before a projection chunk
 constexpr uint32_t kIdescProj = make_idesc_bf16(128, 64);
 
 struct TcFusedParams {
@@ -187,7 +183,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             mbar_init(BAR(o + FuBars::kGFull), 1);
             mbar_init(BAR(o + FuBars::kGEmpty), 4);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FuBars::kWFull + i), 1); mbar_init(BAR(FuBars::kWEmpty + i), 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FuBars::kWFull + i), 1); mbar_init(BAR(FuBars::kWEmpty + i), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -229,114 +225,152 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             FU_TFLUSH(8, true);
         }
     } else if (warp == 1 || warp == 2) {
-        // ===================== MMA issuer of window tile t =====================
-        // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic); one
-        // elected lane issues the tcgen05 instructions.  Descriptors are base + small offsets.
+        // ===================== conv1 MMA issuer of window tile t =====================
+        // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic); one elected lane issues the
+        // tcgen05 instructions.  Nothing but conv1 blocks lives here: what this warp executes between "ring slot free" and
+        // "MMAs queued" is on the critical path of the accumulator ring (A/B with -DB2CNN_MMA_PAD: 32 dependent dummy
+        // instructions per block cost the kernel 16 %), so the projection MMAs -- which used to sit in this loop and block
+        // it while the epilogue's pieces were not ready -- are issued by warp 3, and the descriptors of a block are ready
+        // before its slot is waited for.
         const int t = warp - 1;
         const int o = t * FuBars::kPerTile;
         FU_TDECL();
         const uint64_t a_base = desc_sw128_kmajor(smem_u32(sA_of(t, 0, 0)));
         const uint64_t b_base = desc_none_kmajor(smem_u32(sBm), 128, 256);
-        const uint64_t w_base = desc_none_kmajor(smem_u32(sW), 128, 256);
-        const uint32_t a_lo0 = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
-        const uint32_t b_lo0 = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
-        const uint32_t w_lo0 = (uint32_t)w_base, w_hi = (uint32_t)(w_base >> 32);
         const uint32_t tcol = tmem_base + t * 256;
-        int gi = 0, gm = 0, it = 0;                         // tiles, chunks, items done so far
+        int gi = 0;                                         // tiles done so far (all items): stage = gi & 1
         uint32_t rpar = 0;                                  // bit s: parity of the number of uses of accumulator-ring slot s
-        // m: chunk of the current item, gmm: its global number (A buffer / W stage = gmm & 1)
-        auto issue_proj = [&](int m, int gmm) {
-            const int u = gmm & 1, ph = (gmm >> 1) & 1;
-            { FU_T0();
-            mbar_wait_parked(BAR(FuBars::kWFull + u), ph);
-            mbar_wait_parked(BAR(o + FuBars::kPFull + u), ph);
-            if (m == 0) mbar_wait_parked(BAR(o + FuBars::kGEmpty), (it & 1) ^ 1);   // the previous item's gates left TMEM
-            FU_TACC(7, lane == 0); }
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t d = tcol + 192;
-                const uint32_t a0 = tcol + 128 + u * 24;
-                const uint32_t w0 = w_lo0 + u * (kFuWChunkBytes >> 4);
-                // piece pairs (feature piece, weight piece) with fp + wp <= 2: hh hm mh hl lh mm
-                umma_ts(d, a0 + 0, w0 + 0 * 128, w_hi, kIdescProj, m != 0);
-                umma_ts(d, a0 + 0, w0 + 1 * 128, w_hi, kIdescProj, 1);
-                umma_ts(d, a0 + 8, w0 + 0 * 128, w_hi, kIdescProj, 1);
-                umma_ts(d, a0 + 0, w0 + 2 * 128, w_hi, kIdescProj, 1);
-                umma_ts(d, a0 + 16, w0 + 0 * 128, w_hi, kIdescProj, 1);
-                umma_ts(d, a0 + 8, w0 + 1 * 128, w_hi, kIdescProj, 1);
-                umma_commit(BAR(o + FuBars::kPEmpty + u));
-                umma_commit(BAR(FuBars::kWEmpty + u));
-            }
-            __syncwarp();
-        };
+        uint64_t bdesc[C * SPLITS];                         // loop-invariant band-matrix descriptors
+#pragma unroll
+        for (int i = 0; i < C * SPLITS; ++i) bdesc[i] = b_base + (uint64_t)(i * (kTcBBytes >> 4));
 #ifdef B2CNN_TIMING
         const long long tm0 = clock64();
 #endif
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const Item g = item_geom(item);
-        const int J = g.J, nchunks = g.nchunks;
-        int m_done = 0, n = 0;
-        for (int j = 0; j < J; ++j) {
-            const int s = gi & 1, slot = j & 3;              // ring slots restart with every item, their phases do not
-            if (j >= 8 + kFuLag && ((j - kFuLag) & 7) == 0) { issue_proj(m_done, gm + m_done); ++m_done; }
+        int j = 0;
+#pragma unroll 1
+        for (int i = 0; i < g.ntiles; ++i, ++gi) {
+            const int s = gi & 1;
+            {
+                FU_T0();
 #if B2CNN_MMA_SPIN
-            if (n == 0) mbar_wait(BAR(o + FuBars::kFull + s), (gi >> 1) & 1);
-            mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((rpar >> slot) & 1) ^ 1);
+                mbar_wait(BAR(o + FuBars::kFull + s), (gi >> 1) & 1);
 #else
-            { FU_T0(); if (n == 0) mbar_wait_parked(BAR(o + FuBars::kFull + s), (gi >> 1) & 1); FU_TACC(5, lane == 0); }
-            { FU_T0(); mbar_wait_parked(BAR(o + FuBars::kTEmpty + slot), ((rpar >> slot) & 1) ^ 1); FU_TACC(6, lane == 0); }
+                mbar_wait_parked(BAR(o + FuBars::kFull + s), (gi >> 1) & 1);
 #endif
-            rpar ^= 1u << slot;
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t d = tcol + slot * 32;
-                const uint32_t a_s = a_lo0 + (uint32_t)(s * C) * (kTcABytes >> 4) + n;
-#if B2CNN_ABLATE != 3
-                // the piece-MMAs of a (block, channel) share their A slice through the collector buffer
-                // (fill / use / lastuse) instead of re-reading 4 KB of shared memory per piece
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const uint32_t a_c = a_s + c * (kTcABytes >> 4);
-                    const uint32_t b_c = b_lo0 + (c * SPLITS) * (kTcBBytes >> 4);
-                    umma_ss_coll<kFuCollector ? 1 : 0>(d, a_c, a_hi, b_c, b_hi, kIdesc, c != 0);
-                    if constexpr (SPLITS == 3) umma_ss_coll<kFuCollector ? 2 : 0>(d, a_c, a_hi, b_c + (kTcBBytes >> 4), b_hi, kIdesc, 1);
-                    umma_ss_coll<kFuCollector ? 3 : 0>(d, a_c, a_hi, b_c + (SPLITS - 1) * (kTcBBytes >> 4), b_hi, kIdesc, 1);
-                }
-#else
-                (void)d; (void)a_s;
-#endif
-                umma_commit(BAR(o + FuBars::kTFull + slot));
+                FU_TACC(5, lane == 0);
             }
-            __syncwarp();
-            if (++n == kTcBlocks) { n = 0; ++gi; }
+            const uint64_t a_stage = a_base + (uint64_t)((uint32_t)(s * C) * (kTcABytes >> 4));
+#pragma unroll 1
+            for (int n = 0; n < kTcBlocks; ++n, ++j) {
+                const int slot = j & 3;                     // ring slots restart with every item, their phases do not
+                uint64_t a_c[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) a_c[c] = a_stage + (uint64_t)(c * (kTcABytes >> 4) + n);
+                const uint32_t d = tcol + slot * 32;
+                {
+                    FU_T0();
+#if B2CNN_MMA_SPIN
+                    mbar_wait(BAR(o + FuBars::kTEmpty + slot), ((rpar >> slot) & 1) ^ 1);
+#else
+                    mbar_wait_parked(BAR(o + FuBars::kTEmpty + slot), ((rpar >> slot) & 1) ^ 1);
+#endif
+                    FU_TACC(6, lane == 0);
+                }
+                rpar ^= 1u << slot;
+#ifdef B2CNN_MMA_PAD                                  // experiment: what one extra dispatch slot per block in the MMA-issue warps costs
+                {
+                    uint32_t pad = (uint32_t)j;
+#pragma unroll
+                    for (int z = 0; z < B2CNN_MMA_PAD; ++z) asm volatile("lop3.b32 %0, %0, %0, %0, 0xc0;" : "+r"(pad));
+                    if (pad == 0xdeadbeefu) rpar ^= 16u;
+                }
+#endif
+                tc_fence_after();
+                if (elect_one()) {
+#if B2CNN_ABLATE != 3
+                    // the piece-MMAs of a (block, channel) share their A slice through the collector buffer
+                    // (fill / use / lastuse) instead of re-reading 4 KB of shared memory per piece
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        umma_ss_coll64<kFuCollector ? 1 : 0>(d, a_c[c], bdesc[c * SPLITS], kIdesc, c != 0);
+                        if constexpr (SPLITS == 3) umma_ss_coll64<kFuCollector ? 2 : 0>(d, a_c[c], bdesc[c * SPLITS + 1], kIdesc, 1);
+                        umma_ss_coll64<kFuCollector ? 3 : 0>(d, a_c[c], bdesc[c * SPLITS + SPLITS - 1], kIdesc, 1);
+                    }
+#endif
+                    umma_commit(BAR(o + FuBars::kTFull + slot));
+                }
+                __syncwarp();
+            }
         }
-        for (; m_done < nchunks; ++m_done) issue_proj(m_done, gm + m_done);
-        if (elect_one()) umma_commit(BAR(o + FuBars::kGFull));
-        __syncwarp();
-        gm += nchunks; ++it;
         }
 #ifdef B2CNN_TIMING
         if (lane == 0) atomicAdd(&g_fu_timing[4], (unsigned long long)(clock64() - tm0));
 #endif
         FU_TFLUSH(4, lane == 0);
     } else if (warp == 3) {
-        // ===================== W_ih chunk producer (and TMEM allocator) =====================
-        // Separate from the window-tile producer: a chunk may only be refilled after BOTH window
-        // tiles projected the chunk two back, and that wait must never delay the next A-tile request.
-        if (lane == 0) {
-            int gm = 0;                                     // chunks requested so far (all items): stage = gm & 1
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item g = item_geom(item);
-                const uint8_t *wsrc = p.wpack + (size_t)g.r * p.chunks_per_cta * kFuWChunkBytes;
-                for (int m = 0; m < g.nchunks; ++m, ++gm) {
-                    const int u = gm & 1;
-                    mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((gm >> 1) & 1) ^ 1);
-                    mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
-                    bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), wsrc + (size_t)m * kFuWChunkBytes, kFuWChunkBytes,
-                                 BAR(FuBars::kWFull + u));
+        // ===================== W_ih chunk producer + projection MMA issuer (and TMEM allocator) =====================
+        // Per 16-position chunk: request the NEXT chunk of packed W_ih (its stage is free once the projection two chunks back
+        // has completed), then, for each window tile, wait for the epilogue's three bf16 pieces and issue the six
+        // projection MMAs (A in TMEM).  The whole warp runs the loop, one elected lane issues.
+        FU_TDECL();
+        const uint64_t w_base = desc_none_kmajor(smem_u32(sW), 128, 256);
+        const uint32_t w_lo0 = (uint32_t)w_base, w_hi = (uint32_t)(w_base >> 32);
+        int gm = 0, gl = 0, it = 0;                         // chunks projected / chunks requested (all items); items done
+        auto request_chunk = [&](const uint8_t *src) {      // chunk number gl -> stage gl & 1
+            const int u = gl & 1;
+            mbar_wait_parked(BAR(FuBars::kWEmpty + u), ((gl >> 1) & 1) ^ 1);
+            if (lane == 0) {
+                mbar_expect_tx(BAR(FuBars::kWFull + u), kFuWChunkBytes);
+                bulk_load_1d(smem_u32(sW + u * kFuWChunkBytes), src, kFuWChunkBytes, BAR(FuBars::kWFull + u));
+            }
+            __syncwarp();
+            ++gl;
+        };
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            const Item g = item_geom(item);
+            const uint8_t *wsrc = p.wpack + (size_t)g.r * p.chunks_per_cta * kFuWChunkBytes;
+            if (gl == gm) request_chunk(wsrc);              // very first chunk of the CTA (later items: requested one chunk ahead)
+            for (int m = 0; m < g.nchunks; ++m, ++gm) {
+                // one chunk ahead: the next chunk of this item, or the first chunk of the next item
+                if (m + 1 < g.nchunks) {
+                    request_chunk(wsrc + (size_t)(m + 1) * kFuWChunkBytes);
+                } else if (item + (int)gridDim.x < p.n_items) {
+                    const Item gn = item_geom(item + (int)gridDim.x);
+                    request_chunk(p.wpack + (size_t)gn.r * p.chunks_per_cta * kFuWChunkBytes);
+                }
+                const int u = gm & 1, ph = (gm >> 1) & 1;
+                { FU_T0(); mbar_wait_parked(BAR(FuBars::kWFull + u), ph); FU_TACC(7, lane == 0); }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int o = t * FuBars::kPerTile;
+                    { FU_T0();
+                    mbar_wait_parked(BAR(o + FuBars::kPFull + u), ph);
+                    if (m == 0) mbar_wait_parked(BAR(o + FuBars::kGEmpty), (it & 1) ^ 1);   // the previous item's gates left TMEM
+                    FU_TACC(7, lane == 0); }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t tcol = tmem_base + t * 256;
+                        const uint32_t d = tcol + 192;
+                        const uint32_t a0 = tcol + 128 + u * 24;
+                        const uint32_t w0 = w_lo0 + u * (kFuWChunkBytes >> 4);
+                        // piece pairs (feature piece, weight piece) with fp + wp <= 2: hh hm mh hl lh mm
+                        umma_ts(d, a0 + 0, w0 + 0 * 128, w_hi, kIdescProj, m != 0);
+                        umma_ts(d, a0 + 0, w0 + 1 * 128, w_hi, kIdescProj, 1);
+                        umma_ts(d, a0 + 8, w0 + 0 * 128, w_hi, kIdescProj, 1);
+                        umma_ts(d, a0 + 0, w0 + 2 * 128, w_hi, kIdescProj, 1);
+                        umma_ts(d, a0 + 16, w0 + 0 * 128, w_hi, kIdescProj, 1);
+                        umma_ts(d, a0 + 8, w0 + 1 * 128, w_hi, kIdescProj, 1);
+                        umma_commit(BAR(o + FuBars::kPEmpty + u));
+                        if (t == 1) umma_commit(BAR(FuBars::kWEmpty + u));          // both tiles' MMAs read this W stage
+                        if (m == g.nchunks - 1) umma_commit(BAR(o + FuBars::kGFull));
+                    }
+                    __syncwarp();
                 }
             }
         }
+        FU_TFLUSH(4, lane == 0);
     } else {
         // ===================== epilogue: thread == window =====================
         // Software-pipelined over three steps.  Iteration jj runs
