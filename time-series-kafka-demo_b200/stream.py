@@ -86,7 +86,7 @@ def assemble_windows_gpu(record: NumericsRecord, device="cuda", dtype=None):
     lib = capi.load_library()
     dev = torch.device(device)
     if dev.type != "cuda":
-        raise RuntimeError("assemble_windows_gpu needs a CUDA device; there is no CPU fallback (use assemble_windows)")
+        raise RuntimeError("assemble_windows_gpu needs a CUDA device; there is no CPU fallback")
     dtype = dtype or torch.float32
     if dtype not in (torch.float32, torch.bfloat16):
         raise RuntimeError("dtype must be torch.float32 or torch.bfloat16")
