@@ -351,8 +351,13 @@ def oracle_parity(model, x, ages, y, n_check):
     xs = x[idx.to(x.device)].float().cpu()
     ags = ages[idx.to(ages.device)].cpu()
     t0 = time.perf_counter()
-    torch.set_num_threads(max(1, min(8, usable_cpus()[0])))
+    # ONE thread: torch's multi-threaded GEMV over the 18745 LSTM inputs splits the reduction by thread, and how many threads
+    # the OpenMP runtime actually hands out varies from run to run on a busy box -- seen once as a parity figure of 8.4e-6
+    # instead of 1.6e-6 for bit-identical GPU results (scripts/cross_process_check.sh); single-threaded the oracle is reproducible
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
     want = O.ref_independent(ref, xs, ags).double()
+    torch.set_num_threads(nt)
     got = y[idx.to(y.device)].cpu().double()
     err = (got - want).abs()
     rel = err / want.abs().clamp_min(1e-30)
