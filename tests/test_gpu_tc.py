@@ -99,6 +99,51 @@ def test_tc_nan_inf_windows_are_recomputed_exactly():
     assert np.nanmax(np.abs(fg - fw)) < 2e-5
 
 
+def test_tc_flag_state_is_clean_between_calls():
+    """The NaN-exception flag state lives in the handle and is put back to zero by the head kernel instead of a
+    per-call memset: calls with different flagged windows, clean calls, another stream (workspace copy + memset),
+    a sequence-mode call (no cleaning head) and a different batch size in between must all match the oracle."""
+    ref, m = _pair(3, 7504)
+    base = tskd_b200.synth.make_windows(300, 3, 7504, "normal", seed=9, dtype=torch.bfloat16)
+    ages = tskd_b200.synth.make_ages(300, seed=9)
+    clean_want = O.ref_independent(ref, base.float(), ages).numpy()
+
+    def run(bad, n=300, stream=None):
+        x = base[:n].clone()
+        for b, c, i, v in bad:
+            x[b, c, i] = v
+        want = O.ref_independent(ref, x.float(), ages[:n]).numpy() if bad else clean_want[:n]
+        if stream is None:
+            got = m.predict(x.to(DEV), ages[:n].to(DEV)).cpu().numpy()
+        else:
+            xd, ad = x.to(DEV), ages[:n].to(DEV)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(stream):
+                got = m.predict(xd, ad)
+            stream.synchronize()
+            got = got.cpu().numpy()
+        assert m.last_path == "tensorcore"
+        assert np.array_equal(np.isnan(want), np.isnan(got)), bad
+        ok = ~np.isnan(want)
+        assert rel_err(got[ok], want[ok]) <= TOL
+        return got
+
+    inf, nan = float("inf"), float("nan")
+    g0 = run([])
+    run([(5, 0, 100, inf), (257, 2, 7000, inf), (299, 1, 7503, nan)])
+    g1 = run([])                                    # the flags of 5 / 257 / 299 must be gone
+    assert np.array_equal(g0, g1)
+    run([(5, 1, 3000, inf), (6, 0, 0, inf)])        # a window flagged before, and a new one
+    run([(100, 0, 50, inf)], n=140)                 # other batch size
+    side = torch.cuda.Stream()
+    run([(7, 2, 4000, inf)], stream=side)           # not the owning stream: workspace copy
+    seq = m(base[:24].to(DEV), ages[:24].to(DEV)).cpu().numpy()      # sequence mode: no cleaning head, memset next time
+    assert rel_err(seq, O.ref_sequence(ref, base[:24].float(), ages[:24]).numpy()) <= TOL
+    run([(8, 0, 1234, inf), (299, 2, 5, inf)])
+    g2 = run([])
+    assert np.array_equal(g0, g2)
+
+
 @pytest.mark.parametrize("kind,C,W,B,dist", [
     ("mycnn5", 3, 7500, 150, "normal"),     # W % 8 == 4: rows staged into a 16-byte-pitch scratch for TMA
     ("mycnn5", 3, 37500, 20, "physio"),

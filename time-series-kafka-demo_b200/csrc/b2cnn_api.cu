@@ -465,9 +465,13 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
         if (n < 0) return fail(B2CNN_ECUDA, std::string("fp32 stream kernel: ") + err);
         launches += n;
         if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
-        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, B, age, n_age, apply_sigmoid, out, st, &err)
+        // the head kernel is the last reader of the call's exception list: it also puts the handle's flag state back to zero
+        const bool cleans = indep && h->tc.cur_own;
+        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, B, age, n_age, apply_sigmoid, out, st, &err,
+                                            cleans ? h->tc.cur_count : nullptr, h->tc.cur_flags, h->tc.cur_list)
                   : launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
         if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
+        if (cleans) h->tc.flags_clean = true;
         launches += n;
         if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }
         h->last_launches = launches; h->last_path = B2CNN_PATH_STREAM;
@@ -481,9 +485,13 @@ static int forward_device(b2cnn_handle *h, const void *x, int dtype, int64_t B, 
         if (n < 0) return fail(B2CNN_ECUDA, std::string("tensor-core fused kernel: ") + err);
         launches += n;
         if (prof) CU_TRY(cudaEventRecord(h->ev_stage[1], st));
-        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, B, age, n_age, apply_sigmoid, out, st, &err)
+        // the head kernel is the last reader of the call's exception list: it also puts the handle's flag state back to zero
+        const bool cleans = indep && h->tc.cur_own;
+        n = indep ? launch_reduce_lstm_head(d, h->hw, partial, slices, B, age, n_age, apply_sigmoid, out, st, &err,
+                                            cleans ? h->tc.cur_count : nullptr, h->tc.cur_flags, h->tc.cur_list)
                   : launch_lstm_head(d, h->hw, gates, B, age, n_age, mode, apply_sigmoid, out, st, &err);
         if (n < 0) return fail(B2CNN_ECUDA, std::string("head: ") + err);
+        if (cleans) h->tc.flags_clean = true;
         launches += n;
         if (prof) { CU_TRY(cudaEventRecord(h->ev_stage[2], st)); h->ev_valid = true; }
         h->last_launches = launches; h->last_path = B2CNN_PATH_TENSORCORE;

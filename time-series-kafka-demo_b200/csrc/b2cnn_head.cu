@@ -168,8 +168,18 @@ head_independent_kernel(const float *__restrict__ gates0, HeadWeights hw, const 
 __global__ void __launch_bounds__(256)
 head_reduce_independent_kernel(const float *__restrict__ part, int slices, HeadWeights hw, const float *__restrict__ age,
                                int64_t n_age, float coef, int apply_sigmoid, float *__restrict__ out, int64_t B,
-                               const int *__restrict__ win_list, const int *__restrict__ win_count) {
+                               const int *__restrict__ win_list, const int *__restrict__ win_count,
+                               int *__restrict__ clean_count, int *__restrict__ clean_flags, const int *__restrict__ clean_list) {
     __shared__ float s_w1[kHidden * kGates];               // W_ih_l1 transposed: s_w1[k * 64 + row], conflict-free per k
+    // Last consumer of the call's exception list (the re-computation that read it ran before this kernel): put the
+    // handle's flag state back to all-zero -- exactly the flags the streaming kernel set, and the count -- so the next
+    // call needs no memset.  Nothing in this kernel reads them.
+    if (clean_count != nullptr && blockIdx.x == 0) {
+        const int n = *clean_count;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) clean_flags[clean_list[i]] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) *clean_count = 0;
+    }
     for (int i = threadIdx.x; i < kGates * kHidden; i += blockDim.x) s_w1[(i & 15) * kGates + (i >> 4)] = __ldg(hw.wih1 + i);
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -290,9 +300,11 @@ int launch_reduce_gates(const float *partial, int slices, int64_t B, const HeadW
 
 // independent windows: slice reduction + LSTM cells + Linear + age scale in one launch
 int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, int64_t B,
-                            const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err) {
+                            const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err,
+                            int *clean_count, int *clean_flags, const int *clean_list) {
     head_reduce_independent_kernel<<<(unsigned)((B * 16 + 255) / 256), 256, 0, st>>>(partial, slices, hw, age, n_age, d.age_coef,
-                                                                                  apply_sigmoid, out, B, nullptr, nullptr);
+                                                                                  apply_sigmoid, out, B, nullptr, nullptr,
+                                                                                  clean_count, clean_flags, clean_list);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     return 1;

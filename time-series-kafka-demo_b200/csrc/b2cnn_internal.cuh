@@ -114,7 +114,8 @@ int launch_lstm_head(const Dims &d, const HeadWeights &hw, const float *gates, i
                      int64_t n_age, int mode, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
 
 int launch_reduce_lstm_head(const Dims &d, const HeadWeights &hw, const float *partial, int slices, int64_t B,
-                            const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err);
+                            const float *age, int64_t n_age, int apply_sigmoid, float *out, cudaStream_t st, const char **err,
+                            int *clean_count = nullptr, int *clean_flags = nullptr, const int *clean_list = nullptr);
 
 int choose_ksplit(int64_t B, int L, int num_sms);
 

@@ -47,6 +47,10 @@ constexpr uint32_t kIdesc = make_idesc_bf16(128, 32);
 static thread_local const char *g_tc_err = "";
 const char *tc_error() { return g_tc_err; }
 
+#ifndef B2CNN_OWN_FLAGS
+#define B2CNN_OWN_FLAGS 1          // NaN-exception flag state owned by the handle and cleaned by the head kernel: no per-call memset (TcState)
+#endif
+constexpr int64_t kOwnFlagCap = 65536;   // windows per call served by the handle's own flag state (512 KB); larger batches use the workspace copy
 constexpr int kTcM = 128;          // windows per CTA == UMMA M
 constexpr int kTcAdv = 56;         // conv1 positions (= samples) a tile advances
 constexpr int kTcBlocks = 7;       // 8-position blocks per 64-sample tile
@@ -316,6 +320,18 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
     s.fused_ready = false;
     if (!arch_ok(d) && !arch1_ok(d)) return 0;   // not an error: this shape takes the generic path
     if (!get_encode()) return 0;
+#if B2CNN_OWN_FLAGS
+    if (!s.d_flagstate) {
+        const int64_t cap = kOwnFlagCap;
+        if (cudaMalloc(reinterpret_cast<void **>(&s.d_flagstate), sizeof(int) * (2 * cap + 16)) == cudaSuccess &&
+            cudaMemset(s.d_flagstate, 0, sizeof(int) * (2 * cap + 16)) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess) {
+            s.flag_cap = cap; s.flags_clean = true;
+        } else {
+            cudaFree(s.d_flagstate); s.d_flagstate = nullptr; s.flag_cap = 0;    // not an error: the workspace copy is used
+            (void)cudaGetLastError();
+        }
+    }
+#endif
     // band matrices: piece sp of T_c[k][(s,o)] = w1[o][c][k-s], stored as UMMA K-major
     // no-swizzle core matrices: byte = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2, n = s*4+o.
     //   d_bmats   [C][3][1 KB]  three bf16 pieces (hi/mid/lo: the full 24-bit fp32 mantissa)
@@ -381,6 +397,8 @@ int tc_prepare(TcState &s, const Dims &d, const ConvWeights &cw, const float *d_
 }
 
 void tc_release(TcState &s) {
+    cudaFree(s.d_flagstate);
+    s.d_flagstate = nullptr; s.flag_cap = 0; s.flags_clean = false; s.owner_set = false;
     cudaFree(s.d_bmats);
     cudaFree(s.d_bmats2);
     cudaFree(s.d_wpack);
@@ -559,6 +577,28 @@ int tc_partial_slices(const TcState &s) {
     return s.stream_ready && s.n_ranges_s > s.n_ranges ? s.n_ranges_s : s.n_ranges;
 }
 
+// Where this call keeps count | flags | list: the handle's own, already-zero copy (see TcState) or the head of the
+// workspace, zeroed here.  count and flags are adjacent in both, the list needs no zeroing.
+static int flag_bufs(TcState &s, void *ws, int64_t B, cudaStream_t st, bool cleaning_head_follows, const char **err) {
+    bool own = false;
+#if B2CNN_OWN_FLAGS
+    if (s.d_flagstate && B <= s.flag_cap && cleaning_head_follows) {
+        if (!s.owner_set) { s.owner_set = true; s.owner_stream = st; }
+        own = s.owner_stream == st;
+    }
+#endif
+    if (own) {
+        s.cur_count = s.d_flagstate; s.cur_flags = s.cur_count + 16; s.cur_list = s.cur_flags + s.flag_cap;
+        if (!s.flags_clean && cudaMemsetAsync(s.cur_count, 0, sizeof(int) * (s.flag_cap + 16), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+        s.flags_clean = false;                    // until the cleaning head kernel of this call has been launched
+    } else {
+        s.cur_count = reinterpret_cast<int *>(ws); s.cur_flags = s.cur_count + 16; s.cur_list = s.cur_flags + B;
+        if (cudaMemsetAsync(s.cur_count, 0, sizeof(int) * (B + 16), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+    }
+    s.cur_own = own;
+    return 0;
+}
+
 static int make_tmap(const Dims &d, const void *x, int64_t pitch, int64_t B, CUtensorMap *tm, const char **err) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
     cuuint64_t gdim[3] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)B};
@@ -577,10 +617,9 @@ int tc_fused_gates(TcState &s, const Dims &d, const ConvWeights &cw, const HeadW
                    float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err,
                    bool reduce_here, int *slices_out) {
     (void)feats;
-    // scratch ints: count | flags [B] | list [B]  (count and flags are zeroed by ONE memset; the list needs none)
-    int *count = reinterpret_cast<int *>(ws);
-    int *flags = count + 16, *list = flags + B;
-    if (cudaMemsetAsync(count, 0, sizeof(int) * (B + 16), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+    // scratch ints: count | flags | list  (the handle's own zero-between-calls copy, or the head of the workspace)
+    if (flag_bufs(s, ws, B, st, !reduce_here, err) != 0) return -1;
+    int *count = s.cur_count, *flags = s.cur_flags, *list = s.cur_list;
     int staged = 0;
     int64_t pitch = d.XP;
     const void *xin = tc_stage_input(d, x, B, reinterpret_cast<char *>(ws) + flags_bytes(B), &pitch, &staged, st);
@@ -663,9 +702,8 @@ int tc_stream_gates(TcState &s, const Dims &d, const ConvWeights &cw, const Head
                     float *feats, float *partial, float *gates, void *ws, int num_sms, cudaStream_t st, const char **err,
                     bool reduce_here, int *slices_out) {
     (void)feats;
-    int *count = reinterpret_cast<int *>(ws);
-    int *flags = count + 16, *list = flags + B;
-    if (cudaMemsetAsync(count, 0, sizeof(int) * (B + 16), st) != cudaSuccess) { *err = "memset flags"; return -1; }
+    if (flag_bufs(s, ws, B, st, !reduce_here, err) != 0) return -1;
+    int *count = s.cur_count, *flags = s.cur_flags, *list = s.cur_list;
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) { *err = "x must be 16-byte aligned for TMA"; return -1; }
     CUtensorMap tm;
     {

@@ -17,6 +17,19 @@ struct TcState {
     bool has_v1 = false;         // tc_frontend_kernel (features out) exists for this geometry (MyCNN5 only)
     bool fused_ready = false;    // fused conv + projection kernel usable (C <= 3)
     int64_t opt_fused = 1;
+    // Flag state of the streaming kernels' NaN exception path (count | flags [cap] | list [cap]) owned by the handle:
+    // it is all-zero between calls -- the head kernel that consumes a call's list clears exactly what the call set --
+    // so the per-call memset of the workspace copy (one more stream operation and dependent-launch gap per step)
+    // disappears.  Only calls on the stream that first used it take it (one stream = serialised); calls on any other
+    // stream, batches beyond the capacity and sequence-mode calls keep the workspace copy + memset.
+    int *d_flagstate = nullptr;
+    int64_t flag_cap = 0;
+    bool flags_clean = false;    // host-side: the last call on the owning stream ended with the cleaning head kernel
+    bool owner_set = false;
+    cudaStream_t owner_stream = nullptr;
+    // what the current call uses (read by the caller of tc_*_gates to hand the cleaning job to the head kernel)
+    int *cur_count = nullptr, *cur_flags = nullptr, *cur_list = nullptr;
+    bool cur_own = false;
 };
 
 
