@@ -586,7 +586,7 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # committed ncu captures under profiles/ (None until a capture exists for that path).
 TRAFFIC = {"generic": 1.846642e9 + 0.297926e9,      # profiles/r01_generic_frontend_ncu_full.txt (features written to HBM)
-           "tensorcore": 1.974306e9 + 0.034638e9,   # profiles/r02_persist_fused_ncu_full.txt (halo re-reads + gate partials)
+           "tensorcore": 1.974513e9 + 0.032842e9,   # profiles/r02_final2_fused_ncu_full.txt (halo re-reads + gate partials)
            "stream": 3.801502e9 + 0.034493e9}       # profiles/r01_final_stream_ncu_full.txt (fp32 windows)
 
 if __name__ == "__main__":
