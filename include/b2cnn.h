@@ -8,7 +8,10 @@
  * binds; INTEGRATION.md shows the stub.  Plain pointers and sizes only -- no torch types.
  *
  * Ownership: the caller owns x / age / out / workspace; the library owns only its packed
- * weight buffers (and, for b2cnn_forward_host, its pinned/device staging buffers).
+ * weight buffers, 512 KB of NaN-exception state allocated with them (flags of the windows the
+ * tensor-core kernels hand to the exact path; zero between calls, used by calls on the first
+ * stream a handle sees -- other streams use a copy in the workspace) and, for b2cnn_forward_host,
+ * its pinned/device staging buffers.  A handle serves one call at a time.
  * b2cnn_forward makes no allocation and is asynchronous on `stream`.
  * Errors: every call returns 0 on success or a B2CNN_E* code; b2cnn_last_error() returns a
  * thread-local message.  There is no CPU fallback anywhere in this library.
