@@ -191,6 +191,23 @@ def test_error_behaviour():
         m(torch.zeros(1, 10, 120, device=DEV), torch.tensor([50.0], device=DEV))
 
 
+def test_empty_batch_matches_reference():
+    """model(x, a) on zero windows raises in the reference (nn.LSTM rejects a zero-length sequence, bin/models.py:30);
+    the per-row loop over zero rows scores nothing (bin/predictStream.py:70) -> predict() returns an empty tensor."""
+    ref, m = _pair("mycnn5", 10, 120)
+    x0 = torch.zeros(0, 10, 120)
+    with pytest.raises(RuntimeError):
+        ref(x0, torch.zeros(0))
+    with pytest.raises(RuntimeError):
+        m(x0.to(DEV), torch.zeros(0, device=DEV))
+    with pytest.raises(RuntimeError):
+        m.predict(x0.to(DEV), 65.0, mode="sequence")
+    out = m.predict(x0.to(DEV), 65.0)
+    assert tuple(out.shape) == (0,) and out.dtype == torch.float32 and out.device.type == "cuda"
+    with pytest.raises(RuntimeError, match="expected input"):
+        m.predict(torch.zeros(0, 9, 120, device=DEV), 65.0)
+
+
 def test_host_path_equals_device_path():
     ref, m = _pair("mycnn5", 3, 7500)
     x = tskd_b200.synth.make_windows(700, 3, 7500, "normal", seed=9, dtype=torch.bfloat16)   # > 1 chunk of 64 MiB? (31 MB) -> single; force more below

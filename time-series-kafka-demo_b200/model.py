@@ -345,6 +345,11 @@ class B200MyCNN(nn.Module):
         m = capi.MODE_INDEPENDENT if mode == "independent" else capi.MODE_SEQUENCE
         if mode not in ("independent", "sequence"):
             raise ValueError("mode must be 'independent' or 'sequence'")
+        if B == 0 and mode == "independent":
+            # the per-row loop over zero rows scores nothing (bin/predictStream.py:70); model(x, a) itself raises on an
+            # empty batch (nn.LSTM rejects a zero-length sequence) and so does forward() / mode="sequence"
+            self._check_x(window_tensor)
+            return torch.empty(0, dtype=torch.float32, device=window_tensor.device)
         if age.numel() not in (1, B):
             raise RuntimeError(f"age must be a scalar or have {B} elements")
         return self._run(window_tensor, age, m, return_prob)

@@ -54,7 +54,8 @@ class NumericsRecord:
 
     @classmethod
     def from_wfdb_files(cls, hea_path: str, dat_path: str) -> "NumericsRecord":
-        lines = [l.split() for l in open(hea_path).read().strip().splitlines() if not l.startswith("#")]
+        with open(hea_path) as f:
+            lines = [l.split() for l in f.read().strip().splitlines() if l.strip() and not l.startswith("#")]
         n_sig = int(lines[0][1])
         fs = float(lines[0][2].split("/")[0])
         names, gains, bases = [], [], []
@@ -242,13 +243,25 @@ def replay_stream(model, records: Sequence[NumericsRecord], subject_ids: Sequenc
     turned into the batched dispatch: all records (same sampling rate and length, one per patient) are fed trigger by
     trigger into a PatientRing and every trigger costs ONE ``predict()`` over ``[P, 10, 120]``.  Returns the
     ``predictions`` rows (db/init.sql:24-28) of all patients, trigger-major."""
-    import torch
     P = len(records)
+    if P == 0:
+        return []
+    if len(subject_ids) != P:
+        raise RuntimeError(f"replay_stream: {P} records but {len(subject_ids)} subject ids")
     fs, n, n_sig = records[0].fs, records[0].raw.shape[0], records[0].raw.shape[1]
     if any(r.fs != fs or r.raw.shape != (n, n_sig) for r in records):
         raise RuntimeError("replay_stream: the records of one ring share sampling rate, length and signal count")
     dev = _model_device(model)
     ring = PatientRing(P, n_sig, fs, device=dev)
+    try:
+        return _replay_ring(model, ring, records, subject_ids, ages, samples_per_trigger, dev)
+    finally:
+        ring.close()                                  # the native ring is freed on error paths too
+
+
+def _replay_ring(model, ring, records, subject_ids, ages, samples_per_trigger, dev):
+    import torch
+    P, fs, n = len(records), records[0].fs, records[0].raw.shape[0]
     for p, r in enumerate(records):
         ring.set_record_signals(p, r)
     per = samples_per_trigger or max(1, int(round(STRIDE_S * fs)))
@@ -268,7 +281,6 @@ def replay_stream(model, records: Sequence[NumericsRecord], subject_ids: Sequenc
         for p in range(P):
             if not np.isnan(prob[p]):                                     # predictStream.py:171 drops NaN results
                 rows.append((int(subject_ids[p]), t0, float(prob[p])))
-    ring.close()
     return rows
 
 

@@ -37,6 +37,10 @@ class B200Trainer:
                  mode: str = "sequence", dropout: float = 0.1, seed: int = 0):
         if model.arch.affine or model.arch.act_id != 0:
             raise NotImplementedError("training covers the reference's tanh stack (bin/models.py:23,26) without the affine variant")
+        if mode not in ("sequence", "independent"):
+            raise ValueError("mode must be 'sequence' or 'independent'")
+        if not 0.0 <= float(dropout) < 1.0:
+            raise ValueError("dropout must be in [0, 1)")
         dev = model._device()
         if dev.type != "cuda":
             raise RuntimeError("B200Trainer needs the model on a CUDA device (there is no CPU fallback)")
@@ -75,7 +79,7 @@ class B200Trainer:
             return None, None
         keep = 1.0 - self.dropout
         dev = self._params.device
-        m1 = torch.bernoulli(torch.full((B, 4, self._p1), keep, device=dev), generator=self._gen) / keep
+        m1 = torch.bernoulli(torch.full((B, self.model.arch.c_mid, self._p1), keep, device=dev), generator=self._gen) / keep
         m2 = torch.bernoulli(torch.full((B, self.model.arch.l_out), keep, device=dev), generator=self._gen) / keep
         return m1, m2
 
@@ -95,10 +99,12 @@ class B200Trainer:
         m1, m2 = masks if masks is not None else self.draw_masks(B)
         if m1 is not None:
             m1 = m1.to(dev, torch.float32).contiguous()
-            assert tuple(m1.shape) == (B, 4, self._p1), (tuple(m1.shape), (B, 4, self._p1))
+            if tuple(m1.shape) != (B, a.c_mid, self._p1):
+                raise RuntimeError(f"dropout mask 1 must be {(B, a.c_mid, self._p1)}, got {tuple(m1.shape)}")
         if m2 is not None:
             m2 = m2.to(dev, torch.float32).contiguous()
-            assert tuple(m2.shape) == (B, a.l_out)
+            if tuple(m2.shape) != (B, a.l_out):
+                raise RuntimeError(f"dropout mask 2 must be {(B, a.l_out)}, got {tuple(m2.shape)}")
         need = self._lib.b2cnn_train_workspace_bytes(ctypes.byref(self._cfg), B)
         if need < 0:
             capi.check(capi.EINVAL, "b2cnn_train_workspace_bytes")
