@@ -113,6 +113,20 @@ def test_binary_frame_round_trip_and_validation():
         S.pack_frame([1], adc)
 
 
+def test_binary_frame_header_counts_cannot_wrap_the_size_check():
+    """An untrusted header whose counts multiply to 2^64 bytes (2^24 patients x 2^31 samples x 64 signals x 8 bytes)
+    must not pass the length check of a 64 MB frame: the size is formed in 128-bit arithmetic."""
+    lib = capi.load_library()
+    n_pat, n_new, n_sig = 1 << 24, 1 << 31, 64
+    head = struct.pack("<IHHIIIIQ", capi.FRAME_MAGIC, 1, capi.SAMPLES_F64, n_pat, n_new, n_sig, 0, 0)
+    assert (8 * n_pat * n_new * n_sig) % (1 << 64) == 0
+    frame = head + bytes(4 * n_pat)                       # header + ids: exactly the size a wrapped product describes
+    buf = ctypes.create_string_buffer(frame, len(frame))
+    hd, a, b = capi.FrameHeader(), ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = lib.b2cnn_frame_check(ctypes.addressof(buf), len(frame), ctypes.byref(hd), ctypes.byref(a), ctypes.byref(b))
+    assert rc == capi.EINVAL and "header describes" in capi.last_error()
+
+
 # ------------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_gpu_decoder_rebuilds_the_physical_record_from_sendstream_messages():

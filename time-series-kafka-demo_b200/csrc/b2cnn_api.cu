@@ -1,6 +1,7 @@
 // b2cnn_api.cu -- the extern "C" boundary declared in include/b2cnn.h.
 // Replaces the reference's `model = torch.load(...); model.eval()` (bin/predictStream.py:36-37)
 // and `output = model(x, age)` (bin/predictStream.py:157) with plain-pointer entry points.
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -236,7 +237,9 @@ extern "C" int b2cnn_frame_check(const void *frame, int64_t bytes, b2cnn_frame_h
         return fail(B2CNN_EINVAL, "b2cnn_frame_check: bad kind / shape");
     const int64_t esz = hd.kind == B2CNN_SAMPLES_ADC16 ? 2 : 8;
     const int64_t ids = sizeof hd, smp = (ids + 4ll * hd.n_patients + 7) / 8 * 8;
-    const int64_t need = smp + esz * hd.n_patients * hd.n_new * hd.n_sig;
+    // the header is untrusted input: three 32-bit counts can wrap a 64-bit product, so the size is formed in 128 bits
+    const unsigned __int128 need128 = (unsigned __int128)smp + (unsigned __int128)esz * hd.n_patients * hd.n_new * hd.n_sig;
+    const int64_t need = need128 > (unsigned __int128)INT64_MAX ? INT64_MAX : (int64_t)need128;
     if (bytes != need) {
         char buf[128];
         snprintf(buf, sizeof buf, "b2cnn_frame_check: frame is %lld bytes, its header describes %lld", (long long)bytes, (long long)need);
