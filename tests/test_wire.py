@@ -143,6 +143,9 @@ def test_gpu_decoder_rebuilds_the_physical_record_from_sendstream_messages():
     # malformed and out-of-range messages are counted, not mis-parsed; a signal without a message stays NaN
     frame, bad = S.decode_sample_messages([b"[0, 81.0]", b"[1, oops]", b"[2 81.0]", b"[3, 1e99]", b"[9, 5.0]"], [0, 0, 0, 0, 0], 1, 4, "cuda:0")
     assert bad == 3 and frame.cpu().numpy()[0, 0] == 81.0 and np.isnan(frame.cpu().numpy()[0, 1:]).all()
+    # a row outside the frame (caller error) is dropped, not written: the frame is the tail of a larger buffer here
+    frame, bad = S.decode_sample_messages([b"[0, 1.0]", b"[1, 2.0]", b"[2, 3.0]"], [0, 1, -1], 1, 4, "cuda:0")
+    assert bad == 0 and frame.cpu().numpy()[0, 0] == 1.0 and np.isnan(frame.cpu().numpy()[0, 1:]).all()
 
 
 @pytest.mark.gpu

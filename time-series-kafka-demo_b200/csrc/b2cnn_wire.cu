@@ -121,7 +121,7 @@ __host__ __device__ double parse_number(const uint8_t *s, int64_t &i, int64_t en
 // value = "[<int>, <number>]"  (bin/sendStream.py:62)
 __global__ void decode_pairs_kernel(const uint8_t *__restrict__ bytes, const int64_t *__restrict__ offsets, int64_t n_msgs,
                                     int *__restrict__ idx_out, double *__restrict__ val_out, const int64_t *__restrict__ row_of_msg,
-                                    double *__restrict__ frame, int n_sig, int *__restrict__ n_bad) {
+                                    double *__restrict__ frame, int64_t frame_rows, int n_sig, int *__restrict__ n_bad) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_msgs) return;
     int64_t i = offsets[t];
@@ -146,7 +146,11 @@ __global__ void decode_pairs_kernel(const uint8_t *__restrict__ bytes, const int
     if (status) { idx = -1; v = nan(""); atomicAdd(n_bad, 1); }
     if (idx_out) idx_out[t] = idx;
     if (val_out) val_out[t] = v;
-    if (frame && row_of_msg && idx >= 0 && idx < n_sig && row_of_msg[t] >= 0) frame[row_of_msg[t] * n_sig + idx] = v;
+    // the signal index comes from the message and the row from the caller: neither may leave the frame
+    if (frame && row_of_msg && idx >= 0 && idx < n_sig) {
+        const int64_t row = row_of_msg[t];
+        if (row >= 0 && row < frame_rows) frame[row * n_sig + idx] = v;
+    }
 }
 
 // value = "[v0,v1,...]"  (bin/processStream.py:128 to_json(collect_list(...)), read back by bin/predictStream.py:241)
@@ -196,7 +200,7 @@ int wire_decode_pairs(const uint8_t *bytes, const int64_t *offsets, int64_t n_ms
         fill_nan_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(frame, n);      // a signal without a message is missing
     }
     if (e == cudaSuccess && n_msgs > 0)
-        decode_pairs_kernel<<<(unsigned)((n_msgs + 127) / 128), 128, 0, st>>>(bytes, offsets, n_msgs, idx_out, val_out, row_of_msg, frame, n_sig, n_bad);
+        decode_pairs_kernel<<<(unsigned)((n_msgs + 127) / 128), 128, 0, st>>>(bytes, offsets, n_msgs, idx_out, val_out, row_of_msg, frame, frame_rows, n_sig, n_bad);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return B2CNN_ECUDA; }
     return B2CNN_OK;
