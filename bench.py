@@ -371,6 +371,84 @@ def oracle_parity(model, x, ages, y, n_check):
             "oracle": "oracle/mycnn_torch.py per-window loop, torch CPU fp32", "seconds": time.perf_counter() - t0}
 
 
+def production_shape_block(dev, with_cpu):
+    """NOT the headline: the reference's production call shape (bin/predictStream.py:105,157, config.cfg:23) -- one
+    [1,10,120] window per patient row -- through the same public API: latency of the single call with device and with host
+    tensors, and all patients of a trigger as ONE predict() over [P,10,120]; each with an in-run check against the oracle
+    and, beside it, the reference class itself timed single-threaded on this host (462 us/call)."""
+    import tskd_b200
+    from oracle import mycnn_torch as O
+    from oracle import ref_models
+    m = tskd_b200.B200MyCNN(tskd_b200.ARCH_PRESETS["mycnn5"]).to(dev)
+    ref = O.make_ref(O.ARCH_MYCNN5, seed=0)
+    m.load_state_dict(ref.state_dict())
+    blk = {"shape": "[P,10,120] fp32, MyCNN5 (the checkpoint's own geometry)", "weights": "default init, seed 0"}
+
+    def host_us(fn, n):
+        for _ in range(max(20, n // 20)):
+            fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / n * 1e6
+
+    g = torch.Generator().manual_seed(7)
+    x1h = torch.randn(1, 10, 120, generator=g) * 20 + 80
+    a1h = torch.tensor([65.0])
+    x1, a1 = x1h.to(dev), a1h.to(dev)
+    with torch.no_grad():
+        want1 = float(ref(x1h, a1h))
+    got1 = float(m(x1, a1)[0])
+    blk["single_call"] = {"device_tensors_us": host_us(lambda: m(x1, a1), 3000),
+                          "call_plan_us": host_us(m.call_plan(x1, a1), 3000),
+                          "host_tensors_us": host_us(lambda: m(x1h, a1h), 1000),
+                          "launches_per_call": int(m.gpu_launches), "path": m.last_path,
+                          "rel_err_vs_oracle": abs(got1 - want1) / max(abs(want1), 1e-30),
+                          "note": "back-to-back calls, wall clock / n; host_tensors = H2D + kernel + D2H per call as predictStream.py:155-160 does it"}
+    trig = {}
+    for P in (256, 4096, 32768):
+        xp = (torch.randn(P, 10, 120, generator=g) * 20 + 80).to(dev)
+        ap_ = (torch.rand(P, generator=g) * 70 + 18).to(dev)
+        for _ in range(5):
+            yp = m.predict(xp, ap_)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(50):
+            yp = m.predict(xp, ap_)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = e0.elapsed_time(e1) / 50 * 1e3
+        n_chk = min(P, 128)
+        want = O.ref_independent(ref, xp[:n_chk].cpu(), ap_[:n_chk].cpu()).double()
+        got = yp[:n_chk].cpu().double()
+        rel = float((got - want).abs().max() / want.abs().max().clamp_min(1e-6))     # as tests/conftest.py rel_err
+        trig[str(P)] = {"us_per_call": us, "windows_per_s": P / (us / 1e6), "launches_per_call": int(m.gpu_launches),
+                        "max_rel_vs_oracle": rel, "n_checked": n_chk}
+    blk["trigger_batch"] = trig
+    blk["parity_ok"] = bool(blk["single_call"]["rel_err_vs_oracle"] <= PARITY_TOL and all(t["max_rel_vs_oracle"] <= PARITY_TOL for t in trig.values()))
+    if with_cpu:
+        cls = ref_models.reference_class()
+        cpu_m = ref if cls is None else cls().eval()
+        if cls is not None:
+            cpu_m.load_state_dict(ref.state_dict(), strict=False)
+        nt = torch.get_num_threads()
+        torch.set_num_threads(1)
+        with torch.no_grad():
+            for _ in range(50):
+                cpu_m(x1h, a1h)
+            t0 = time.perf_counter()
+            for _ in range(1000):
+                cpu_m(x1h, a1h)
+            us_cpu = (time.perf_counter() - t0) / 1000 * 1e6
+        torch.set_num_threads(nt)
+        blk["reference_cpu"] = {"us_per_call": us_cpu, "threads": 1, "kind": "reference" if cls is not None else "port",
+                                "note": "output = model(x_arr, a_arr) with [1,10,120] under no_grad, torch CPU fp32 (bin/predictStream.py:157)"}
+    return blk
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -569,6 +647,14 @@ def main():
                                             "max_abs_diff_vs_headline_logits": float((y2 - y).abs().max()),
                                             "note": "option, not the default: conv1 weights rounded to 16 mantissa bits (two bf16 pieces)"}}
             del m2
+        if world == 1 and args.dtype == "bf16" and args.extra_steps > 0:
+            try:                                        # an extra block never costs the headline line
+                ps = production_shape_block(dev, not args.no_cpu_baseline)
+            except Exception as e:                      # noqa: BLE001
+                ps = {"error": f"{type(e).__name__}: {e}"}
+            out.setdefault("extra", {})["production_shape"] = ps
+            if not ps.get("parity_ok", False):
+                print(f"bench.py: production-shape extra block: {ps}", file=sys.stderr)
         if world == 1 and not args.no_cpu_baseline:
             steps_cpu = 10
             r = cpu_reference_run(steps_cpu, 1, max(5.0, args.cpu_seconds))
