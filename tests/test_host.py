@@ -183,3 +183,24 @@ def test_train_entry_points_validate_without_a_gpu():
     rc = lib.b2cnn_train_step(ctypes.byref(cfg), None, None, None, None, 1, ctypes.byref(opt), 1, None, 4, None, None, 1, None, None,
                               None, None, 0, None)
     assert rc == capi.EINVAL and "null" in capi.last_error()
+
+
+def test_zero_windows_and_trainer_argument_checks_need_no_gpu():
+    """predict() over zero rows scores nothing (the per-row loop of bin/predictStream.py:70) and never reaches the library;
+    the trainer rejects bad arguments before it looks for a device."""
+    import tskd_b200
+    from tskd_b200.trainer import B200Trainer
+    m = tskd_b200.B200MyCNN(tskd_b200.ARCH_PRESETS["mycnn5"])
+    out = m.predict(torch.zeros(0, 10, 120), 65.0)
+    assert tuple(out.shape) == (0,) and out.dtype == torch.float32
+    with pytest.raises(RuntimeError, match="expected input"):
+        m.predict(torch.zeros(0, 9, 120), 65.0)
+    with pytest.raises(ValueError, match="mode"):
+        m.predict(torch.zeros(0, 10, 120), 65.0, mode="rows")
+    with pytest.raises(ValueError, match="mode"):
+        B200Trainer(m, mode="rows")
+    with pytest.raises(ValueError, match="dropout"):
+        B200Trainer(m, dropout=1.0)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            B200Trainer(m)
